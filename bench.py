@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""bench.py -- audio Msamples/s demodulated over batched streams (BASELINE.json).
+
+One "step" = one pass of the hot path (the batched rx loop: per-stream frame
+search + tone correlation + rx state machine, src/minimodem.c:1137-1463 over
+src/fsk.c:449-538) over one batch of synthetic streams.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+N>1 is launched by torchrun (one rank per GPU); streams shard across ranks with
+no data-path collective (weak scaling: every rank demodulates its own batch);
+NCCL carries only the broadcast of the derived plan (fsk_b200_rx_params).
+
+`value`   : whole-job Msamples/s, inputs resident in HBM, timed with CUDA events.
+`e2e`     : the same metric through the host-buffer C-ABI call
+            (fsk_b200_rx_batch_host): pinned host samples -> device -> records
+            back on the host, copies inside the timed region.
+`roofline`: algorithmic bytes (4 + 20/frame_nsamples per sample)
+            over the rx kernel's own CUDA-event time, against the measured HBM
+            copy bandwidth (MEASURED_PEAKS.json).
+`cpu_baseline` / `--impl reference`: the reference's CPU implementation (the
+            unmodified src/fsk.c compiled into oracle/_ref behind the oracle's
+            rx-loop restatement; else the oracle port) on the host cores, on a
+            bounded sample of the same workload.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="1200")
+    ap.add_argument("--rate", type=int, default=48000)
+    ap.add_argument("--streams", type=int, default=65536, help="streams per GPU")
+    ap.add_argument("--nsamples", type=int, default=192000, help="samples per stream (4 s at 48 kHz)")
+    ap.add_argument("--e2e-streams", type=int, default=8192)
+    ap.add_argument("--cpu-streams", type=int, default=0, help="CPU sample size (0 = 4 per core)")
+    ap.add_argument("--lanes", type=int, default=0)
+    ap.add_argument("--wpb", type=int, default=0)
+    ap.add_argument("--ring", type=int, default=0)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return "Bell202-like %s baud, %d Hz float32, %d synthetic streams x %d samples per GPU" % (
+        a.mode, a.rate, a.streams, a.nsamples)
+
+
+# --------------------------------------------------------------------------
+# CPU arm (the reference on the host cores)
+# --------------------------------------------------------------------------
+def cpu_streams_on_host(a, nstreams):
+    """Synthetic streams for the CPU arm, made on the CPU by the oracle's TX
+    restatement (same signal model and payload statistics as the device generator)."""
+    import orc
+    m = orc.Mode(a.mode, sample_rate=a.rate)
+    d = m.derived()
+    one = int(orc.lib().orc_tx_nsamples(C.byref(m.tx_config(1.0, 4096, True)), 1))
+    zero = int(orc.lib().orc_tx_nsamples(C.byref(m.tx_config(1.0, 4096, True)), 2)) - one
+    nwords = max(1, (a.nsamples - (one - zero) - int(d.nsamples_per_bit)) // zero)
+    rng = np.random.default_rng(20260922)
+    x = np.zeros((nstreams, a.nsamples), np.float32)
+    for s in range(nstreams):
+        words = rng.integers(32, 127, nwords, dtype=np.uint32) & ((1 << m.n_data_bits) - 1)
+        w = orc.tx_words(m, words, 1.0, 4096, True)
+        lead = int(rng.integers(0, int(d.nsamples_per_bit)))
+        k = min(w.size, a.nsamples - lead)
+        x[s, lead:lead + k] = w[:k]
+    return m, x, nwords
+
+
+def cpu_measure(a, x, mode, steps=1, warmup=0):
+    import orc
+    cores = len(os.sched_getaffinity(0))
+    kind = "reference" if orc.have_ref() else "port"
+    best = []
+    for i in range(warmup + steps):
+        t = time.perf_counter()
+        total, fps, _ = orc.rx_many(mode, x, nsamples=a.nsamples, nthreads=cores, kind=kind)
+        dt = time.perf_counter() - t
+        if i >= warmup:
+            best.append(dt)
+    dt = sum(best) / len(best)
+    return dict(value=x.shape[0] * a.nsamples / dt / 1e6, unit="Msamples/s", cores=cores, kind=kind,
+                sample="%d streams x %d samples, %d threads, %s" % (
+                    x.shape[0], a.nsamples, cores,
+                    "unmodified src/fsk.c (oracle/_ref, FFT stand-in, not FFTW) behind the oracle rx loop"
+                    if kind == "reference" else "oracle port (two-bin direct DFT)"),
+                frames=int(total)), dt
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import orc
+    cores = len(os.sched_getaffinity(0))
+    n = a.cpu_streams or max(16, min(512, 4 * cores))
+    mode, x, _ = cpu_streams_on_host(a, n)
+    cb, dt = cpu_measure(a, x, mode, steps=a.steps, warmup=a.warmup)
+    line = {
+        "impl": "reference", "metric": "audio Msamples/s demodulated (batched streams)",
+        "value": cb["value"], "unit": "Msamples/s", "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "sample_per_step": cb["sample"]},
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for ln in self.p.stdout:
+            self.rows.append([c.strip() for c in ln.split(",")])
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=2)
+        except Exception:
+            self.p.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for k, nm in enumerate(names):
+                    if r[5 + k].lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    import minimodem_b200 as mm
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- plan: derived on rank 0, broadcast over NCCL (the only collective on the path)
+    nbytes = C.sizeof(mm.RxParams)
+    blob = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+    cfg = mm.rx_config_for_mode(a.mode, a.rate)
+    if rank == 0:
+        p0 = mm.rx_params(cfg)
+        blob.copy_(torch.frombuffer(bytearray(bytes(p0)), dtype=torch.uint8))
+    if world > 1:
+        dist.broadcast(blob, src=0)
+    params = mm.RxParams.from_buffer_copy(bytes(blob.cpu().numpy().tobytes()))
+    eng = mm.RxEngine(params)
+    if a.lanes or a.wpb or a.ring:
+        eng.tune(a.lanes, a.wpb, a.ring)
+
+    # ---- workload, generated on the device in the reference transmitter's signal model
+    S, n = a.streams, a.nsamples
+    free, _ = torch.cuda.mem_get_info(dev)
+    stride = (n + 3) & ~3
+    shrunk = False
+    while S * stride * 4 > 0.80 * free and S > 1024:
+        S //= 2
+        shrunk = True
+    tcfg = mm.tx_config_from(cfg)
+    spb = float(params.nsamples_per_bit)
+    frame = params.frame_nsamples
+    nwords = max(1, (n - int(4 * spb) - int(spb)) // frame)
+    gen = torch.Generator(device="cpu").manual_seed(20260922 + rank)
+    mask = (1 << params.n_data_bits) - 1
+    words = (torch.randint(32, 127, (S, nwords), generator=gen, dtype=torch.int32) & mask).to(dev)
+    lead = torch.randint(0, max(1, int(spb)), (S,), generator=gen, dtype=torch.int32).to(dev)
+    x = torch.empty((S, stride), dtype=torch.float32, device=dev)
+    mm.tx_batch(tcfg, words, n, lead_in=lead, out=x, stride=stride)
+    torch.cuda.synchronize()
+
+    max_frames = eng.max_frames(n)
+    frames = torch.empty((S, max_frames, 5), dtype=torch.int32, device=dev)
+    states = torch.zeros((S, 8), dtype=torch.int32, device=dev)
+
+    def step():
+        states.zero_()
+        eng.rx_batch(x, nsamples=n, max_frames=max_frames, frames=frames, states=states)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(a.warmup):
+        step()
+    barrier()
+    launches0 = mm.launch_count()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(a.steps)]
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0.record()
+    for i in range(a.steps):
+        states.zero_()
+        kev[i][0].record()
+        eng.rx_batch(x, nsamples=n, max_frames=max_frames, frames=frames, states=states)
+        kev[i][1].record()
+    t1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = mm.launch_count() - launches0
+    ms_total = t0.elapsed_time(t1)
+    ms_kernel = sum(e0.elapsed_time(e1) for e0, e1 in kev) / a.steps
+    ms_step = ms_total / a.steps
+    if world > 1:
+        t = torch.tensor([ms_step, ms_kernel], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_step, ms_kernel = float(t[0]), float(t[1])
+
+    # ---- sanity outside the timed region: the work was really done
+    st = mm.states_to_numpy(states)
+    assert (st["done"] == 1).all(), "streams did not finish"
+    nfr = st["nframes"].astype(np.int64)
+    assert nfr.min() >= nwords, ("frames per stream", int(nfr.min()), nwords)
+    fr = mm.frames_to_numpy(frames[:8])
+    shift = (1 if params.nstopbits != 0 else 0) + params.nstartbits
+    w = words[:8].cpu().numpy()
+    for s in range(8):
+        data = ((fr[s, :nfr[s]]["bits_lo"].astype(np.int64)) >> shift) & mask
+        got, want = data.tolist(), (w[s] & mask).tolist()
+        assert any(got[i:i + len(want)] == want for i in range(len(got) - len(want) + 1)), "decode mismatch"
+
+    total_samples = S * n * world
+    value = total_samples / (ms_step * 1e-3) / 1e6
+    bytes_per_sample = 4.0 + 20.0 / frame
+    peak, peak_src = peaks()
+    achieved = S * n * bytes_per_sample / (ms_kernel * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "kernel": "k_rx", "kernel_ms": ms_kernel,
+                "algorithmic_bytes_per_sample": bytes_per_sample}
+
+    # ---- end to end through the host-buffer C ABI call
+    e2e = None
+    if not a.no_e2e:
+        E = min(a.e2e_streams, S)
+        hx = torch.empty((E, stride), dtype=torch.float32, pin_memory=True)
+        hx.copy_(x[:E])
+        hfr = torch.empty((E, max_frames, 5), dtype=torch.int32, pin_memory=True)
+        hst = torch.zeros((E, 8), dtype=torch.int32, pin_memory=True)
+        torch.cuda.synchronize()
+
+        def host_step():
+            hst.zero_()
+            eng.rx_batch_host(hx, nsamples=n, max_frames=max_frames, frames_out=hfr, states_out=hst)
+
+        for _ in range(max(1, a.warmup // 2)):
+            host_step()
+        barrier()
+        tt = time.perf_counter()
+        for _ in range(a.steps):
+            host_step()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - tt) / a.steps
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t[0])
+        hs = hst.numpy().view(mm.STATE_DTYPE).reshape(-1)
+        assert (hs["done"] == 1).all() and np.array_equal(hs["nframes"], st["nframes"][:E])
+        e2e = {"value": E * n * world / dt / 1e6, "unit": "Msamples/s",
+               "h2d_bytes_per_step": int(E * stride * 4 + E * 32),
+               "d2h_bytes_per_step": int(E * max_frames * 20 + E * 32),
+               "streams_per_step": E, "ms_per_step": dt * 1e3,
+               "note": "fsk_b200_rx_batch_host on pinned host buffers; PCIe-bound (4 B/sample in)"}
+
+    # ---- the reference CPU path on this box's host cores (rank 0, N=1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu:
+        try:
+            import orc
+            cores = len(os.sched_getaffinity(0))
+            ncpu = a.cpu_streams or max(16, min(512, 4 * cores))
+            ncpu = min(ncpu, S)
+            hostx = x[:ncpu, :n].cpu().numpy()
+            cpu, _ = cpu_measure(a, np.ascontiguousarray(hostx), orc.Mode(a.mode, sample_rate=a.rate))
+        except Exception as ex:  # the checker is optional for the number, never for the tests
+            cpu = {"value": None, "unit": "Msamples/s", "cores": None, "kind": "unavailable", "sample": repr(ex)}
+
+    if rank == 0:
+        line = {
+            "metric": "audio Msamples/s demodulated (batched streams)",
+            "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(a) + (" (shrunk to %d streams to fit memory)" % S if shrunk else ""),
+                       "streams_per_gpu": S, "nsamples": n, "frame_nsamples": frame,
+                       "l2": "inputs (%.1f GB per GPU) far exceed the 126 MB L2; no flush needed" % (S * stride * 4 / 1e9),
+                       "parallelism": "streams sharded over %d GPU(s); NCCL broadcast of the plan only" % world},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks, "lib": mm.version(),
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

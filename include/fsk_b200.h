@@ -1,0 +1,265 @@
+/*
+ * fsk_b200.h -- C ABI of the B200-native FSK demodulation engine.
+ *
+ * Part 1 is a drop-in for the reference's src/fsk.h (kamalmostafa/minimodem
+ * v0.24): same type name, same public scalar fields, same five functions with
+ * the same signatures and error behaviour, so that the reference's rx loop
+ * (src/minimodem.c:1045, :1265, :1373, :1188, :1219, :1478) links against this
+ * library unchanged.  Part 2 is the batched extension the reference does not
+ * have: many independent audio streams per call, samples resident in HBM.
+ *
+ * Plain C: pointers and sizes only, no CUDA or torch types.  `void *stream`
+ * arguments are CUDA stream handles (cudaStream_t) passed opaquely; NULL is
+ * the default stream.  All reference citations are path:line in the reference
+ * tree.
+ */
+#ifndef FSK_B200_H
+#define FSK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ======================================================================== */
+/* Part 1 -- drop-in for src/fsk.h                                          */
+/* ======================================================================== */
+
+typedef struct fsk_plan fsk_plan;
+
+/* Replaces `struct fsk_plan`, src/fsk.h:30-46.  The scalar fields keep the
+ * reference's names, types and order because the rx loop reads them directly
+ * (fftsize src/minimodem.c:1184; band_width :1203,:1217,:1340; nbands :1210;
+ * b_mark :1340).  The three FFTW members (fftplan, fftin, fftout; src/fsk.h:
+ * 42-44) become opaque engine pointers of the same size. */
+struct fsk_plan {
+    float	sample_rate;
+    float	f_mark;
+    float	f_space;
+    float	filter_bw;	/* declared but never written by the reference either */
+
+    int		fftsize;
+    unsigned int nbands;
+    float	band_width;
+    unsigned int b_mark;
+    unsigned int b_space;
+    void	*engine;	/* was fftwf_plan fftplan: device-side engine state */
+    float	*scratch_in;	/* was float *fftin:  pinned host staging buffer */
+    void	*scratch_out;	/* was fftwf_complex *fftout: pinned result buffer */
+};
+
+/* src/fsk.h:49-55, src/fsk.c:33-95.  NULL + errno=EINVAL (and the reference's
+ * message on stderr) when a tone band falls outside [0, nbands); NULL when the
+ * engine cannot be created (no CUDA device: the library has no CPU fallback). */
+fsk_plan *fsk_plan_new(float sample_rate, float f_mark, float f_space, float filter_bw);
+
+/* src/fsk.h:57-58, src/fsk.c:97-104 */
+void fsk_plan_destroy(fsk_plan *fskp);
+
+/* src/fsk.h:61-71, src/fsk.c:449-538.  `samples` is host memory, borrowed for
+ * the call; the callee reads samples[0 .. try_max_nsamples-1 + span) where span
+ * is the frame's bit windows (the caller guarantees frame_nsamples valid floats
+ * and, like the reference, an allocation that covers the rest).  Out-params are
+ * always written.  Returns the best confidence (0.0 = nothing found; may be
+ * +inf). */
+float fsk_find_frame(fsk_plan *fskp, float *samples, unsigned int frame_nsamples,
+	unsigned int try_first_sample,
+	unsigned int try_max_nsamples,
+	unsigned int try_step_nsamples,
+	float try_confidence_search_limit,
+	const char *expect_bits_string,
+	unsigned long long *bits_outp,
+	float *ampl_outp,
+	unsigned int *frame_start_outp);
+
+/* src/fsk.h:73-75, src/fsk.c:543-581.  Returns the strongest band >= 1 whose
+ * magnitude is >= min_mag_threshold, or -1. */
+int fsk_detect_carrier(fsk_plan *fskp, float *samples, unsigned int nsamples,
+	float min_mag_threshold);
+
+/* src/fsk.h:77-78, src/fsk.c:584-598 */
+void fsk_set_tones_by_bandshift(fsk_plan *fskp, unsigned int b_mark, int b_shift);
+
+/* ======================================================================== */
+/* Part 2 -- batched extension (not in the reference)                       */
+/* ======================================================================== */
+
+#define FSK_B200_MAX_BITS 64	/* assert at src/fsk.c:463 */
+
+/* What the reference's main() derives from `{baudmode}` + options before it
+ * enters the rx loop (src/minimodem.c:819-965).  Fill by hand or with
+ * fsk_b200_rx_config_for_mode(). */
+typedef struct fsk_b200_rx_config {
+    float	sample_rate;		/* :534 */
+    float	data_rate;		/* bfsk_data_rate */
+    float	f_mark, f_space;	/* :900-934, after --inverted :953 */
+    int		inverted;		/* override input only: swap the tones, :953-957 */
+    float	band_width;		/* after the clamp at :960 */
+    unsigned int n_data_bits;
+    int		nstartbits;
+    float	nstopbits;
+    int		invert_start_stop;
+    int		msb_first;
+    int		do_rx_sync;
+    unsigned long long sync_byte;	/* (unsigned long long)-1 = none, :501 */
+    float	confidence_threshold;	/* :513, -c */
+    float	confidence_search_limit; /* :523, -l; raised to the threshold, :964 */
+    char	expect_data_string[FSK_B200_MAX_BITS + 4]; /* "" = build it, :1116-1119 */
+} fsk_b200_rx_config;
+
+/* Restates the baudmode presets, src/minimodem.c:819-965: "rtty", "tdd", "same",
+ * "callerid", "uic-train", "uic-ground", "V.21", or a number of baud.  Fields of
+ * `overrides` that are non-zero (mark, space, band_width, n_data_bits) or >= 0
+ * (nstartbits, nstopbits) take the place of the command-line options -M -S -b
+ * -8/-7/-5 --startbits --stopbits; pass NULL for none.  Returns 0, or -1 for an
+ * unusable mode (data rate 0, > 64 bits per frame). */
+int fsk_b200_rx_config_for_mode(const char *baudmode, float sample_rate,
+	const fsk_b200_rx_config *overrides, fsk_b200_rx_config *out);
+
+/* Everything the rx loop derives once (src/minimodem.c:1037-1131) plus the bit
+ * window geometry fsk_frame_analyze derives per call (src/fsk.c:183,204,465).
+ * Plain data: this is the block that is broadcast to the other GPUs. */
+typedef struct fsk_b200_rx_params {
+    /* plan, src/fsk.c:45-57 */
+    float	sample_rate, f_mark, f_space, band_width;
+    int		fftsize;
+    unsigned int nbands, b_mark, b_space;
+    /* loop constants */
+    float	nsamples_per_bit;	/* :1037 */
+    unsigned int frame_n_bits;		/* :943 (truncating) */
+    unsigned int frame_nsamples;	/* :1113 */
+    unsigned int expect_n_bits;		/* :1118 */
+    unsigned int expect_nsamples;	/* :1131 (truncating) */
+    unsigned int nsamples_overscan;	/* :1105-1108 */
+    unsigned int try_max_nocarrier, try_max_carrier;	/* :1236-1241 */
+    float	confidence_threshold, confidence_search_limit;
+    /* framing, for the host-side bit chop :1415-1428 */
+    unsigned int n_data_bits;
+    int		nstartbits;
+    float	nstopbits;
+    int		msb_first, do_rx_sync;
+    unsigned long long sync_byte;
+    /* bit windows of one frame candidate */
+    float	samples_per_bit;	/* (float)expect_nsamples / expect_n_bits, src/fsk.c:465 */
+    unsigned int bit_nsamples;		/* src/fsk.c:183 */
+    unsigned int bit_begin[FSK_B200_MAX_BITS];	/* src/fsk.c:204,249 */
+    unsigned int span_nsamples;		/* bit_begin[n-1] + bit_nsamples */
+    char	expect_data[FSK_B200_MAX_BITS + 4];
+    char	expect_sync[FSK_B200_MAX_BITS + 4];
+} fsk_b200_rx_params;
+
+/* Fails (-1, errno=EINVAL) like fsk_plan_new when a tone band is out of range. */
+int fsk_b200_rx_params_derive(const fsk_b200_rx_config *cfg, fsk_b200_rx_params *out);
+
+/* One decoded frame, 20 bytes.  `frame_start` is the within-window start the
+ * reference calls frame_start_sample (src/minimodem.c:1257, after refinement);
+ * bit 31 is set on the frame that acquired carrier (:1332-1355), which is also
+ * where the downstream databits decoder is reset (:1351). */
+typedef struct fsk_b200_frame {
+    uint32_t	bits_lo, bits_hi;	/* raw fsk_find_frame bits, LSB first */
+    float	confidence;		/* coarse-search confidence (:1265) */
+    float	amplitude;
+    uint32_t	frame_start;
+} fsk_b200_frame;
+#define FSK_B200_FRAME_ACQUIRED 0x80000000u
+
+/* Per-stream loop state, readable after a run and accepted back to continue a
+ * stream with more audio (streaming use). */
+typedef struct fsk_b200_stream_state {
+    uint64_t	pos;		/* absolute sample index of the next search window */
+    uint32_t	nframes;	/* frame records written so far */
+    uint32_t	carrier;	/* :1081 */
+    uint32_t	noconfidence;	/* :1087 */
+    float	track_amplitude;	/* :1132 */
+    float	peak_confidence;	/* :1133 */
+    uint32_t	done;		/* loop ended: fewer than expect_nsamples remain (:1229) */
+} fsk_b200_stream_state;
+
+typedef struct fsk_b200_engine fsk_b200_engine;
+
+/* Creates an engine on the current CUDA device.  NULL + errno (EINVAL bad
+ * params, ENODEV no usable CUDA device). */
+fsk_b200_engine *fsk_b200_engine_new(const fsk_b200_rx_params *params);
+void fsk_b200_engine_destroy(fsk_b200_engine *e);
+const fsk_b200_rx_params *fsk_b200_engine_params(const fsk_b200_engine *e);
+
+/* Tuning knobs (0 = engine default): lanes per stream (1..32, power of two),
+ * warps per block, ring floats per stream (power of two). */
+int fsk_b200_engine_tune(fsk_b200_engine *e, int lanes_per_stream, int warps_per_block,
+	int ring_floats);
+
+/* Batched fsk_find_frame (src/fsk.c:449-538): one search per stream, all
+ * pointers DEVICE memory.  Stream s reads samples[s*stride + offset[s] ...];
+ * floats at or beyond s*stride + nvalid[s] read as 0.  expect_sel[s] selects
+ * expect_data (0) or expect_sync (1); try_* and limit follow the reference's
+ * arguments.  Outputs: confidence[s], frames[s] (bits, confidence, amplitude,
+ * frame_start).  Asynchronous on `stream`.  Returns 0 or a negative errno. */
+int fsk_b200_find_frame_batch(fsk_b200_engine *e, const float *samples,
+	size_t nstreams, size_t stride, const uint32_t *offset, const uint32_t *nvalid,
+	const uint32_t *try_first, const uint32_t *try_max, const uint32_t *try_step,
+	const float *limit, const uint8_t *expect_sel,
+	fsk_b200_frame *frames, void *stream);
+
+/* Batched rx loop (src/minimodem.c:1137-1463) over whole streams resident in
+ * HBM: stream s is samples[s*stride .. s*stride + nsamples[s]) (nsamples NULL =
+ * all `stride_valid` long).  Frame records go to frames[s*max_frames ...]; a
+ * stream that would overflow max_frames stops with done=0.  `states` (device,
+ * one per stream) must be zeroed for a fresh stream; it is updated in place.
+ * Asynchronous on `stream`.  Returns 0 or a negative errno. */
+int fsk_b200_rx_batch(fsk_b200_engine *e, const float *samples, size_t nstreams,
+	size_t stride, const uint32_t *nsamples, uint32_t nsamples_all,
+	fsk_b200_frame *frames, uint32_t max_frames,
+	fsk_b200_stream_state *states, void *stream);
+
+/* Same, from HOST buffers: copies (pinned or pageable) host streams to the
+ * device in slabs, overlapping copy and demodulation on two CUDA streams, and
+ * copies the records back.  This is the call a host application makes.
+ * Synchronous.  Returns 0 or a negative errno. */
+int fsk_b200_rx_batch_host(fsk_b200_engine *e, const float *host_samples, size_t nstreams,
+	size_t stride, uint32_t nsamples_all,
+	fsk_b200_frame *host_frames, uint32_t max_frames,
+	fsk_b200_stream_state *host_states);
+
+/* Upper bound on frame records a stream of nsamples can produce. */
+uint32_t fsk_b200_max_frames(const fsk_b200_rx_params *p, uint32_t nsamples);
+
+/* src/minimodem.c:1415-1428: frame bits -> the data word handed to the
+ * databits decoder (prev-stop chop, bit_window, optional bit_reverse). */
+unsigned long long fsk_b200_frame_databits(const fsk_b200_rx_params *p, const fsk_b200_frame *f);
+
+/* Device-side synthesis of test streams in the reference transmitter's signal
+ * model (src/minimodem.c:81-250, src/simple-tone-generator.c:107-175; float
+ * samples through a sine table of table_len entries computed by the caller on
+ * the host).  Stream s carries words[s*nwords .. +nwords) after lead_in[s]
+ * samples of silence; writes exactly nsamples_out floats per stream (zero
+ * padded / truncated).  All pointers are device memory. */
+typedef struct fsk_b200_tx_config {
+    float	sample_rate, data_rate, f_mark, f_space;
+    unsigned int n_data_bits;
+    float	nstartbits, nstopbits;
+    int		invert_start_stop, msb_first;
+    unsigned int do_tx_sync_bytes, sync_byte;
+    int		leader_bits, trailer_bits;
+} fsk_b200_tx_config;
+
+/* The float sine table of the reference tone generator
+ * (src/simple-tone-generator.c:53-54): out[i] = mag * sinf((float)M_PI*2*i/len). */
+void fsk_b200_sin_table(float *out, unsigned int len, float mag);
+
+int fsk_b200_tx_batch(const fsk_b200_tx_config *cfg, const float *sin_table, uint32_t table_len,
+	const uint32_t *words, uint32_t nwords, const uint32_t *lead_in,
+	float *samples_out, size_t nstreams, size_t stride, uint32_t nsamples_out, void *stream);
+
+/* Library / build information: "fsk_b200 <version> sm_100a". */
+const char *fsk_b200_version(void);
+/* Number of kernel launches issued by this library in this process. */
+unsigned long long fsk_b200_launch_count(void);
+/* Last error message of the calling thread ("" if none). */
+const char *fsk_b200_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FSK_B200_H */

@@ -10,6 +10,7 @@
 #include <float.h>
 #include <errno.h>
 #include <pthread.h>
+#include <sched.h>
 
 #include "fsk_oracle.h"
 
@@ -341,7 +342,9 @@ int orc_rx_run(const orc_rx_config *cfg, const float *samples, size_t nsamples,
     orc_rx_derived d;
     orc_plan plan;
     int own_plan = 0;
-    memset(res, 0, sizeof(*res));
+    /* res must be zero-initialised before its first use; buffers are reused */
+    res->nframes = res->nreports = res->ncalls = 0;
+    res->n_find_frame_calls = 0;
     orc_rx_derive(cfg, &d);
     if (d.expect_n_bits == 0 || d.expect_n_bits > 64)
 	return -1;
@@ -366,11 +369,20 @@ int orc_rx_run(const orc_rx_config *cfg, const float *samples, size_t nsamples,
     /* widest read the callee can make past samplebuf[0] */
     const size_t touch_max = (size_t)(d.nsamples_per_bit + d.nsamples_overscan) + 2
 	    + d.expect_nsamples + (size_t)d.nsamples_per_bit + 2;
-    float *ring = NULL, *tail = NULL;
-    if (mode == ORC_RX_LITERAL)
-	ring = calloc(S + touch_max, sizeof(float));	/* :1071 (malloc there) */
-    else
-	tail = calloc(2 * touch_max + 8, sizeof(float));
+    /* per-thread scratch, kept across calls (page faults are expensive on VMs) */
+    static __thread float *scratch;
+    static __thread size_t scratch_cap;
+    const size_t want_floats = mode == ORC_RX_LITERAL ? S + touch_max : 2 * touch_max + 8;
+    if (scratch_cap < want_floats) {
+	free(scratch);
+	scratch = malloc(want_floats * sizeof(float));
+	scratch_cap = scratch ? want_floats : 0;
+	if (!scratch)
+	    return -1;
+    }
+    memset(scratch, 0, want_floats * sizeof(float));	/* :1071 (malloc there) */
+    float *ring = mode == ORC_RX_LITERAL ? scratch : NULL;
+    float *tail = mode == ORC_RX_LITERAL ? NULL : scratch;
     size_t samples_nvalid = 0;		/* literal */
     unsigned long long pos = 0;		/* absolute index of samplebuf[0] */
 
@@ -556,8 +568,6 @@ int orc_rx_run(const orc_rx_config *cfg, const float *samples, size_t nsamples,
 	    confidence_total, amplitude_total, (unsigned)res->nframes };
 	PUSH(res, reports, nreports, cap_reports, rp);
     }
-    free(ring);
-    free(tail);
     if (own_plan)
 	orc_plan_free(&plan);
     return 0;
@@ -575,43 +585,73 @@ struct many_job {
     unsigned *frames_per_stream;
     unsigned long long *bits_xor;
     unsigned long long total;
+    orc_plan_new_fn plan_new;
+    orc_find_frame_fn find_frame;
+    orc_plan_destroy_fn plan_destroy;
 };
 
 static void *many_worker(void *arg)
 {
     struct many_job *j = arg;
+    /* spread the workers over the allowed CPUs at once: short runs otherwise stay
+     * packed on one vCPU until the scheduler's load balancer notices */
+    cpu_set_t allowed, one;
+    if (sched_getaffinity(0, sizeof(allowed), &allowed) == 0) {
+	int ncpu = CPU_COUNT(&allowed), want = j->tid % (ncpu ? ncpu : 1), seen = 0;
+	for (int c = 0; c < CPU_SETSIZE; c++) {
+	    if (!CPU_ISSET(c, &allowed))
+		continue;
+	    if (seen++ == want) {
+		CPU_ZERO(&one);
+		CPU_SET(c, &one);
+		pthread_setaffinity_np(pthread_self(), sizeof(one), &one);
+		break;
+	    }
+	}
+    }
     orc_plan plan;
-    if (orc_plan_init(&plan, j->cfg->sample_rate, j->cfg->f_mark, j->cfg->f_space,
+    void *ctx = &plan;
+    orc_find_frame_fn ff = default_find_frame;
+    if (j->plan_new) {
+	ctx = j->plan_new(j->cfg->sample_rate, j->cfg->f_mark, j->cfg->f_space, j->cfg->band_width);
+	ff = j->find_frame;
+	if (!ctx)
+	    return NULL;
+    } else if (orc_plan_init(&plan, j->cfg->sample_rate, j->cfg->f_mark, j->cfg->f_space,
 		j->cfg->band_width) != 0)
 	return NULL;
+    orc_rx_result r;
+    memset(&r, 0, sizeof(r));
     for (size_t s = j->tid; s < j->nstreams; s += j->nthreads) {
-	orc_rx_result r;
 	orc_rx_run(j->cfg, j->samples + s * j->stride, j->nsamples, ORC_RX_FLAT,
-		0.0f, 0, 0, default_find_frame, &plan, &r);
+		0.0f, 0, 0, ff, ctx, &r);
 	unsigned long long x = 0;
 	for (size_t i = 0; i < r.nframes; i++)
 	    x ^= r.frames[i].bits * (i + 1);
 	if (j->frames_per_stream) j->frames_per_stream[s] = (unsigned)r.nframes;
 	if (j->bits_xor) j->bits_xor[s] = x;
 	j->total += r.nframes;
-	orc_rx_result_free(&r);
     }
-    orc_plan_free(&plan);
+    orc_rx_result_free(&r);
+    if (j->plan_new)
+	j->plan_destroy(ctx);
+    else
+	orc_plan_free(&plan);
     return NULL;
 }
 
 unsigned long long orc_rx_many(const orc_rx_config *cfg, const float *samples,
 	size_t nstreams, size_t stride, size_t nsamples, int nthreads,
-	orc_find_frame_fn unused, unsigned *frames_per_stream,
-	unsigned long long *bits_xor_per_stream)
+	orc_plan_new_fn plan_new, orc_find_frame_fn find_frame, orc_plan_destroy_fn plan_destroy,
+	unsigned *frames_per_stream, unsigned long long *bits_xor_per_stream)
 {
-    (void)unused;
     if (nthreads < 1) nthreads = 1;
     pthread_t *th = calloc(nthreads, sizeof(*th));
     struct many_job *jobs = calloc(nthreads, sizeof(*jobs));
     for (int t = 0; t < nthreads; t++) {
 	jobs[t] = (struct many_job){ cfg, samples, nstreams, stride, nsamples, t,
-	    nthreads, frames_per_stream, bits_xor_per_stream, 0 };
+	    nthreads, frames_per_stream, bits_xor_per_stream, 0,
+	    plan_new, find_frame, plan_destroy };
 	pthread_create(&th[t], NULL, many_worker, &jobs[t]);
     }
     unsigned long long total = 0;

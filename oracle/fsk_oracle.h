@@ -153,7 +153,8 @@ typedef struct orc_rx_result {
  * --Xrxnoise quirk (src/simpleaudio-sndfile.c:64-70: a constant -rxnoise DC
  * offset applied to every *requested* frame of each read).  find_frame/ctx
  * NULL = orc_find_frame on an internal plan.  rx_one stops after the first
- * carrier drop (:1310).  Returns 0, or -1 on bad config. */
+ * carrier drop (:1310).  *res must be zero-initialised before its first use
+ * (its buffers are reused by later calls).  Returns 0, or -1 on bad config. */
 int orc_rx_run(const orc_rx_config *cfg, const float *samples, size_t nsamples,
 		int mode, float rxnoise, int rx_one, int want_calls,
 		orc_find_frame_fn find_frame, void *ctx,
@@ -165,11 +166,17 @@ unsigned long long orc_rx_databits(const orc_rx_config *cfg, unsigned long long 
 
 /* Multi-threaded driver for the CPU baseline: demodulates nstreams flat
  * streams (row stride in floats) with nthreads threads, one plan per thread
- * (plans are not re-entrant, src/fsk.h:42-44).  Returns total frames decoded;
- * per-stream frame counts / xor of bits optionally written. */
+ * (plans are not re-entrant, src/fsk.h:42-44), streams round-robin.  With
+ * plan_new/find_frame/plan_destroy NULL the oracle's own two-bin analyzer is
+ * used ("port"); pass the three entry points of oracle/_ref/libfsk_ref.so to
+ * time the unmodified reference src/fsk.c behind the same rx loop
+ * ("reference").  Returns total frames decoded. */
+typedef void *(*orc_plan_new_fn)(float, float, float, float);
+typedef void (*orc_plan_destroy_fn)(void *);
 unsigned long long orc_rx_many(const orc_rx_config *cfg, const float *samples,
 		size_t nstreams, size_t stride, size_t nsamples, int nthreads,
-		orc_find_frame_fn find_frame_factory_unused,
+		orc_plan_new_fn plan_new, orc_find_frame_fn find_frame,
+		orc_plan_destroy_fn plan_destroy,
 		unsigned *frames_per_stream, unsigned long long *bits_xor_per_stream);
 
 /* ---- tx: restates src/minimodem.c:81-250 + src/simple-tone-generator.c -- */

@@ -137,7 +137,8 @@ def lib():
         L.orc_rx_databits.argtypes = [C.POINTER(OrcRxConfig), C.c_ulonglong]
         L.orc_rx_databits.restype = C.c_ulonglong
         L.orc_rx_many.argtypes = [C.POINTER(OrcRxConfig), fp, C.c_size_t, C.c_size_t, C.c_size_t,
-                                  C.c_int, C.c_void_p, C.POINTER(C.c_uint), C.POINTER(C.c_ulonglong)]
+                                  C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.POINTER(C.c_uint), C.POINTER(C.c_ulonglong)]
         L.orc_rx_many.restype = C.c_ulonglong
         L.orc_tx_nsamples.argtypes = [C.POINTER(OrcTxConfig), C.c_size_t]
         L.orc_tx_nsamples.restype = C.c_size_t
@@ -501,3 +502,25 @@ def ref_decode(mode, frames, decoder=None):
         n = fn(buf, 4096, data, mode.n_data_bits)
         out += buf.raw[:n]
     return bytes(out)
+
+
+def rx_many(mode, samples, nsamples=None, nthreads=1, kind="port"):
+    """CPU baseline driver: kind="port" = the oracle's two-bin analyzer, kind="reference" =
+    the unmodified src/fsk.c from oracle/_ref behind the same rx-loop restatement.
+    samples: [nstreams, stride] float32.  Returns (total_frames, frames_per_stream, bits_xor)."""
+    samples = np.ascontiguousarray(samples, np.float32)
+    nstreams, stride = samples.shape
+    n = int(nsamples if nsamples is not None else stride)
+    cfg = mode.rx_config()
+    fps = np.zeros(nstreams, np.uint32)
+    bx = np.zeros(nstreams, np.uint64)
+    pn = ff = pd = None
+    if kind == "reference":
+        R = ref()
+        pn = C.cast(R.fsk_plan_new, C.c_void_p)
+        ff = C.cast(R.fsk_find_frame, C.c_void_p)
+        pd = C.cast(R.fsk_plan_destroy, C.c_void_p)
+    total = lib().orc_rx_many(C.byref(cfg), fptr(samples.reshape(-1)), nstreams, stride, n, int(nthreads),
+                              pn, ff, pd, fps.ctypes.data_as(C.POINTER(C.c_uint)),
+                              bx.ctypes.data_as(C.POINTER(C.c_ulonglong)))
+    return int(total), fps, bx

@@ -1,0 +1,349 @@
+"""Parity tests proper (B200): the CUDA path, called through the C ABI, against
+the oracle on the same inputs -- the reference's own test vectors (golden
+fixtures minted from the unmodified reference CLI), seeded noisy inputs, and
+size-independent properties at larger batch sizes.
+
+Bars: bits / frame_start / decoded bytes bit-exact; confidence and amplitude
+within 1e-4 relative (+ the conditioning term of golden_util.close for
+confidences >> 1, where two correct FFTs already disagree); inf is a class."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import golden_util as gu
+import minimodem_b200 as mm
+import orc
+import refcases
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+def engine_for(case_or_mode, rx=True):
+    if isinstance(case_or_mode, dict):
+        mode, kw = case_or_mode["rx_mode"], case_or_mode["rx_mkw"]
+    else:
+        mode, kw = case_or_mode
+    names = dict(mark="f_mark", space="f_space", bandwidth="band_width", startbits="nstartbits",
+                 stopbits="nstopbits")
+    ov = {names.get(k, k): v for k, v in kw.items() if k != "sample_rate"}
+    cfg = mm.rx_config_for_mode(mode, kw.get("sample_rate", 48000), **ov)
+    return mm.RxEngine(mm.rx_params(cfg)), cfg
+
+
+def pad4(n):
+    return (n + 3) & ~3
+
+
+def rx_on_gpu(eng, streams, lanes=0):
+    """streams: list of 1-D float32 arrays -> list of frame-record arrays."""
+    n = max(len(a) for a in streams)
+    stride = pad4(n)
+    buf = np.zeros((len(streams), stride), np.float32)
+    lens = np.zeros(len(streams), np.int32)
+    for i, a in enumerate(streams):
+        buf[i, :len(a)] = a
+        lens[i] = len(a)
+    if lanes:
+        eng.tune(lanes_per_stream=lanes)
+    d = torch.from_numpy(buf).to(dev())
+    frames, states = eng.rx_batch(d, nsamples=n, nsamples_each=torch.from_numpy(lens).to(dev()))
+    torch.cuda.synchronize()
+    fr = mm.frames_to_numpy(frames)
+    st = mm.states_to_numpy(states)
+    assert (st["done"] == 1).all()
+    return [fr[i, :st["nframes"][i]] for i in range(len(streams))], st
+
+
+def as_oracle_frames(recs):
+    out = []
+    for r in recs:
+        bits = int(r["bits_lo"]) | (int(r["bits_hi"]) << 32)
+        fs = int(r["frame_start"])
+        out.append((bits, np.float32(r["confidence"]), np.float32(r["amplitude"]), fs & 0x7FFFFFFF,
+                    1 if fs & mm.FRAME_ACQUIRED else 0, 0))
+    return out
+
+
+def reports_from(frames, mode, d, final_carrier):
+    """Recompute the NOCARRIER statistics from the frame records, in record order
+    (src/minimodem.c:1324-1330, :1397-1399, :253-291)."""
+    reps, cur = [], None
+    for fr in frames:
+        bits, conf, ampl, start, acquired, _ = fr
+        if acquired:
+            if cur is not None:
+                reps.append(cur)
+            cur = [0, 0, np.float32(0), np.float32(0)]
+            cur[1] += d.frame_nsamples
+        else:
+            cur[1] += d.frame_nsamples + start - d.nsamples_overscan
+        cur[0] += 1
+        cur[2] = np.float32(cur[2] + conf)
+        cur[3] = np.float32(cur[3] + ampl)
+    if cur is not None:     # printed at the drop (:1300) or at exit while carrier is up (:1469)
+        reps.append(cur)
+    return [(r[0], r[1], r[2], r[3], 0) for r in reps]
+
+
+def compare_frames(got, want, what=""):
+    assert len(got) == len(want), (what, len(got), len(want))
+    for i, (a, b) in enumerate(zip(got, want)):
+        assert a[0] == b[0], (what, i, hex(a[0]), hex(b[0]))
+        assert a[3] == b[3] and a[4] == b[4], (what, i, a, b)
+        assert gu.close(a[1], b[1], cond=gu.CONF_COND), (what, i, a[1], b[1])
+        assert gu.close(a[2], b[2]), (what, i, a[2], b[2])
+
+
+# --------------------------------------------------------------------------
+# the reference's own test vectors through the batched rx kernel
+# --------------------------------------------------------------------------
+RX_CASES = [c for c in refcases.ALL]
+
+
+@pytest.mark.parametrize("case", RX_CASES, ids=[c["name"] for c in RX_CASES])
+def test_rx_batch_on_reference_vectors(case):
+    g = gu.load(case["name"])
+    _, rx = gu.modes(case)
+    a = gu.audio(case, g)
+    if case["rxnoise"]:
+        a = (a + np.float32(-0.5) * np.float32(np.float32(case["rxnoise"]) * 2)).astype(np.float32)
+    eng, cfg = engine_for(case)
+    want = orc.rx_run(rx, a, literal=False, rx_one=False)
+    (recs,), st = rx_on_gpu(eng, [a])
+    got = as_oracle_frames(recs)
+    compare_frames(got, want["frames"], case["name"])
+    if orc.have_ref():
+        # byte-identical decode, the reference's own pass criterion (tests/self-test: cmp)
+        frames = got
+        if case["rx_one"]:          # --rx-one: stop at the first carrier drop (:1310)
+            nacq = [i for i, f in enumerate(frames) if f[4]]
+            if len(nacq) > 1:
+                frames = frames[:nacq[1]]
+        assert orc.ref_decode(rx, frames) == bytes(g["stdout"])
+    # stat line (the -P tests grep it for "confidence=inf ... (rate perfect)")
+    d = rx.derived()
+    reps = reports_from(got, rx, d, bool(st["carrier"][0]))
+    lines = [orc.report_line(rx, r) for r in reps]
+    wantl = gu.stat_lines(g)
+    if case["rx_one"]:
+        lines = lines[:1]
+    assert len(lines) >= len(wantl) >= 1
+    fa, fb = lines[0].split(), wantl[0].split()
+    assert fa[:3] == fb[:3] and fa[4:] == fb[4:], (lines[0], wantl[0])
+    assert gu.close(float(fa[3].split("=")[1]), float(fb[3].split("=")[1]), 2e-3, cond=gu.CONF_COND)
+    if case["perfect"]:
+        assert "confidence=inf" in lines[0] and "(rate perfect)" in lines[0]
+
+
+@pytest.mark.parametrize("lanes", [2, 4, 8, 16, 32])
+@pytest.mark.parametrize("name", ["01-self-test-1200", "80-SAME", "small-rtty", "21-rate-slop-308"])
+def test_rx_batch_every_lane_split(name, lanes):
+    case = refcases.BY_NAME[name]
+    g = gu.load(name)
+    _, rx = gu.modes(case)
+    a = gu.audio(case, g)
+    eng, _ = engine_for(case)
+    want = orc.rx_run(rx, a, literal=False)
+    (recs,), _ = rx_on_gpu(eng, [a], lanes=lanes)
+    compare_frames(as_oracle_frames(recs), want["frames"], "%s G=%d" % (name, lanes))
+
+
+# --------------------------------------------------------------------------
+# batched fsk_find_frame vs the oracle (and the compiled reference) on noisy input
+# --------------------------------------------------------------------------
+@pytest.mark.parametrize("mode,kw", [("1200", {}), ("300", {}), ("rtty", dict(sample_rate=8000)),
+                                     ("same", {}), ("12000", {}), ("rtty", {})])
+def test_find_frame_batch_noisy(mode, kw):
+    m = orc.Mode(mode, **kw)
+    d = m.derived()
+    eng, _ = engine_for((mode, kw))
+    rng = np.random.default_rng(99)
+    words = rng.integers(0, 1 << m.n_data_bits, 40, dtype=np.uint32)
+    clean = orc.tx_words(m, words, 1.0, 4096, True)
+    spb = float(d.nsamples_per_bit)
+    plan = orc.Plan(m.sample_rate, m.mark_f, m.space_f, m.band_width)
+    nstreams = 256
+    tmc = int(np.float32(np.float32(spb) * np.float32(0.75) + np.float32(0.5))) + d.nsamples_overscan
+    tmn = int(spb) + d.nsamples_overscan
+    wlen = pad4(tmn + d.expect_nsamples + int(spb) + 8)
+    buf = np.zeros((nstreams, wlen), np.float32)
+    args = np.zeros((nstreams, 5), np.int64)
+    limit = np.zeros(nstreams, np.float32)
+    sel = np.zeros(nstreams, np.uint8)
+    for s in range(nstreams):
+        sigma = (0.0, 0.05, 0.3, 1.0)[s % 4]
+        pos = int(rng.integers(0, clean.size - wlen))
+        w = clean[pos:pos + wlen] + sigma * rng.standard_normal(wlen)
+        buf[s] = w.astype(np.float32)
+        carrier = (s // 4) % 2
+        fine = (s // 8) % 2
+        tmax = tmc if carrier else tmn
+        args[s] = (wlen - (s % 3) * 16, d.nsamples_overscan if carrier else 0, tmax,
+                   max(tmax // (8 if fine else 3), 1), 0)
+        limit[s] = np.inf if fine else 2.3
+        sel[s] = 0 if carrier else 1
+    t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a.astype(dt))).to(dev())
+    frames = eng.find_frame_batch(t(buf, np.float32), t(args[:, 0], np.int32), t(args[:, 1], np.int32),
+                                  t(args[:, 2], np.int32), t(args[:, 3], np.int32), t(limit, np.float32),
+                                  expect_sel=t(sel, np.uint8))
+    torch.cuda.synchronize()
+    fr = mm.frames_to_numpy(frames)
+    n_bad = n_found = 0
+    for s in range(nstreams):
+        nv = int(args[s, 0])
+        w = buf[s].copy()
+        w[nv:] = 0
+        expect = d.expect_data if sel[s] == 0 else d.expect_sync
+        want = plan.find_frame(w, d.expect_nsamples, int(args[s, 1]), int(args[s, 2]), int(args[s, 3]),
+                               float(limit[s]), expect)
+        got_bits = int(fr[s]["bits_lo"]) | (int(fr[s]["bits_hi"]) << 32)
+        ok = (got_bits == want[1] and int(fr[s]["frame_start"]) == want[3]
+              and gu.close(fr[s]["confidence"], want[0], cond=gu.CONF_COND)
+              and gu.close(fr[s]["amplitude"], want[2]))
+        n_found += want[0] > 0
+        if not ok:
+            n_bad += 1
+            assert (s % 4) != 0, (mode, s, fr[s], want)      # clean streams must match exactly
+    assert n_found > nstreams // 8
+    assert n_bad <= 2, n_bad                                   # razor-edge candidate flips only
+
+
+# --------------------------------------------------------------------------
+# the drop-in single-stream API driving the reference's rx loop
+# --------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["small-1200", "small-300", "small-rtty", "small-same",
+                                  "small-1200-float-noise", "70-callerid-mdmf"])
+def test_dropin_find_frame_behind_the_rx_loop(name):
+    """fsk_find_frame (C ABI, host buffers) plugged into the oracle's literal
+    restatement of the reference rx loop, as the unmodified minimodem.c would call it."""
+    case = refcases.BY_NAME[name]
+    g = gu.load(name)
+    _, rx = gu.modes(case)
+    a = gu.audio(case, g)
+    plan = mm.FskPlan(rx.sample_rate, rx.mark_f, rx.space_f, rx.band_width)
+    op = orc.Plan(rx.sample_rate, rx.mark_f, rx.space_f, rx.band_width).p
+    assert (plan.fftsize, plan.nbands, plan.b_mark, plan.b_space) == (op.fftsize, op.nbands, op.b_mark, op.b_space)
+    L = mm.lib()
+
+    def cb(ctx, samples, frame_nsamples, first, tmax, step, limit, expect, bits, ampl, start):
+        return L.fsk_find_frame(plan._p, samples, frame_nsamples, first, tmax, step, limit, expect,
+                                bits, ampl, start)
+
+    got = orc.rx_run(rx, a, literal=True, rxnoise=case["rxnoise"], rx_one=case["rx_one"],
+                     want_calls=True, find_frame=cb)
+    cu, cf, cb_ = g["call_u32"], g["call_f32"], g["call_bits"]
+    assert len(got["calls"]) == len(cb_)
+    for i, c in enumerate(got["calls"]):
+        assert c[7] == int(cb_[i]) and c[9] == int(cu[i, 4]), (i, c)
+        assert gu.close(c[6], cf[i, 1], cond=gu.CONF_COND) and gu.close(c[8], cf[i, 2]), (i, c, cf[i])
+    if orc.have_ref():
+        assert orc.ref_decode(rx, got["frames"]) == bytes(g["stdout"])
+    plan.destroy()
+
+
+def test_dropin_detect_carrier_and_bandshift():
+    plan = mm.FskPlan(48000, 1200, 2200, 200)
+    n = 40
+    t = np.arange(n, dtype=np.float32)
+    x = (0.8 * np.sin(2 * np.pi * 2200 * t / 48000)).astype(np.float32)
+    assert plan.detect_carrier(x, 0.001) == 11          # 2200 Hz / 200 Hz bands
+    assert plan.detect_carrier(np.zeros(n, np.float32), 0.001) == -1
+    if orc.have_ref():
+        rp = orc.RefPlan(48000, 1200, 2200, 200)
+        rng = np.random.default_rng(5)
+        for _ in range(8):
+            y = (x * rng.uniform(0.1, 1) + 0.05 * rng.standard_normal(n)).astype(np.float32)
+            want = orc.ref().fsk_detect_carrier
+            want.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_uint, C.c_float]
+            want.restype = C.c_int
+            assert plan.detect_carrier(y, 0.001) == want(rp.h, orc.fptr(y), n, 0.001)
+    plan.set_tones_by_bandshift(11, -5)                 # src/fsk.c:584-598
+    assert (plan.b_mark, plan.b_space) == (11, 6)
+    assert (plan.f_mark, plan.f_space) == (2200.0, 1200.0)
+    plan.destroy()
+
+
+# --------------------------------------------------------------------------
+# transmitter model on the device: bit-exact with the oracle's restatement
+# --------------------------------------------------------------------------
+@pytest.mark.parametrize("mode,kw", [("1200", {}), ("300", {}), ("rtty", dict(sample_rate=8000)), ("same", {})])
+def test_tx_batch_bit_exact(mode, kw):
+    m = orc.Mode(mode, **kw)
+    eng, cfg = engine_for((mode, kw))
+    rng = np.random.default_rng(3)
+    nstreams, nwords = 64, 12
+    words = rng.integers(0, 1 << m.n_data_bits, (nstreams, nwords), dtype=np.uint32)
+    lead = rng.integers(0, 200, nstreams, dtype=np.uint32)
+    tcfg = mm.tx_config_from(cfg)
+    ref0 = orc.tx_words(m, words[0], 1.0, 4096, True)
+    nout = ref0.size + 260
+    out = mm.tx_batch(tcfg, torch.from_numpy(words.astype(np.int32)).to(dev()), nout,
+                      lead_in=torch.from_numpy(lead.astype(np.int32)).to(dev()))
+    torch.cuda.synchronize()
+    o = out.cpu().numpy()
+    for s in range(nstreams):
+        want = np.zeros(nout, np.float32)
+        w = orc.tx_words(m, words[s], 1.0, 4096, True)
+        want[lead[s]:lead[s] + w.size] = w
+        assert np.array_equal(o[s, :nout], want), s
+
+
+# --------------------------------------------------------------------------
+# size-independent properties on a larger batch
+# --------------------------------------------------------------------------
+@pytest.mark.parametrize("mode,kw,nstreams,nwords", [("1200", {}, 4096, 60), ("rtty", dict(sample_rate=8000), 2048, 20),
+                                                     ("300", {}, 1024, 20), ("same", {}, 2048, 30)])
+def test_roundtrip_property_large_batch(mode, kw, nstreams, nwords):
+    """tx -> rx: every stream decodes exactly the words that were sent, and the same
+    answer comes back for every lane split (results do not depend on the launch shape)."""
+    m = orc.Mode(mode, **kw)
+    d = m.derived()
+    eng, cfg = engine_for((mode, kw))
+    p = eng.params
+    gen = torch.Generator(device="cpu").manual_seed(11)
+    words = torch.randint(0, 1 << m.n_data_bits, (nstreams, nwords), generator=gen, dtype=torch.int32)
+    if m.do_rx_sync:            # the sync byte itself is suppressed by the rx (:1436-1439)
+        words[words == (m.sync_byte & 0xFF)] = 0x55
+    lead = torch.randint(0, int(d.nsamples_per_bit), (nstreams,), generator=gen, dtype=torch.int32)
+    tcfg = mm.tx_config_from(cfg)
+    n1 = int(orc.lib().orc_tx_nsamples(C.byref(m.tx_config(1.0, 4096, True)), nwords))
+    nout = n1 + int(d.nsamples_per_bit) + 8
+    x = mm.tx_batch(tcfg, words.to(dev()), nout, lead_in=lead.to(dev()))
+    results = []
+    for lanes in (0, 32):
+        eng.tune(lanes_per_stream=lanes)
+        frames, states = eng.rx_batch(x, nsamples=nout)
+        torch.cuda.synchronize()
+        results.append((frames.clone(), states.clone()))
+    assert torch.equal(results[0][1], results[1][1])
+    fr = mm.frames_to_numpy(results[0][0])
+    st = mm.states_to_numpy(results[0][1])
+    fr1 = mm.frames_to_numpy(results[1][0])
+    assert (st["done"] == 1).all()
+    w = words.numpy()
+    shift = (1 if m.nstopbits != 0 else 0) + m.nstartbits
+    mask = (1 << m.n_data_bits) - 1
+    for s in range(nstreams):
+        k = int(st["nframes"][s])
+        assert np.array_equal(fr[s, :k], fr1[s, :k]), s
+        data = ((fr[s, :k]["bits_lo"].astype(np.uint64) | (fr[s, :k]["bits_hi"].astype(np.uint64) << np.uint64(32)))
+                >> np.uint64(shift)) & np.uint64(mask)
+        if m.do_rx_sync:
+            data = data[data != (m.sync_byte & mask)]
+        # the leader/trailer may add idle frames around the payload; the payload must be inside
+        got = data.astype(np.int64).tolist()
+        want = (w[s] & mask).tolist()
+        assert any(got[i:i + len(want)] == want for i in range(len(got) - len(want) + 1)), (s, got, want)
+    # cross-check a sample of streams frame by frame against the oracle
+    xs = x[:16].cpu().numpy()
+    for s in range(16):
+        want = orc.rx_run(m, xs[s, :nout], literal=False)
+        compare_frames(as_oracle_frames(fr[s, :st["nframes"][s]]), want["frames"], "stream %d" % s)
