@@ -164,17 +164,31 @@ typedef struct fsk_b200_frame {
     uint32_t	frame_start;
 } fsk_b200_frame;
 #define FSK_B200_FRAME_ACQUIRED 0x80000000u
+/* A record whose frame_start is FSK_B200_FRAME_REPORT is not a frame but the
+ * statistics of the carrier session that just ended -- what the reference hands
+ * to report_no_carrier() when it drops carrier (src/minimodem.c:1298-1307):
+ * bits = carrier_nsamples, confidence = confidence_total, amplitude =
+ * amplitude_total; nframes_decoded is the number of frame records since the
+ * last ACQUIRED one.  A session still open when the stream ends is reported in
+ * fsk_b200_stream_state instead (the reference prints it at exit, :1469-1474). */
+#define FSK_B200_FRAME_REPORT 0xFFFFFFFFu
 
 /* Per-stream loop state, readable after a run and accepted back to continue a
  * stream with more audio (streaming use). */
 typedef struct fsk_b200_stream_state {
     uint64_t	pos;		/* absolute sample index of the next search window */
-    uint32_t	nframes;	/* frame records written so far */
+    uint32_t	nframes;	/* records written so far (frames + session reports) */
     uint32_t	carrier;	/* :1081 */
     uint32_t	noconfidence;	/* :1087 */
     float	track_amplitude;	/* :1132 */
     float	peak_confidence;	/* :1133 */
     uint32_t	done;		/* loop ended: fewer than expect_nsamples remain (:1229) */
+    /* statistics of the open carrier session (:1082-1085) */
+    uint64_t	carrier_nsamples;
+    float	confidence_total;
+    float	amplitude_total;
+    uint32_t	nframes_decoded;
+    uint32_t	reserved[3];
 } fsk_b200_stream_state;
 
 typedef struct fsk_b200_engine fsk_b200_engine;

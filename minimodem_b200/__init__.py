@@ -11,5 +11,5 @@ from .api import (  # noqa: F401
     LIB_PATH, Frame, RxConfig, RxParams, RxEngine, FskPlan, StreamState, TxConfig,
     build, lib, rx_config_for_mode, rx_params, frame_databits, max_frames, tx_batch,
     version, launch_count, sin_table, frames_to_numpy, states_to_numpy, tx_config_from,
-    FRAME_DTYPE, STATE_DTYPE, FRAME_ACQUIRED, EXPORTS,
+    FRAME_DTYPE, STATE_DTYPE, STATE_WORDS, FRAME_ACQUIRED, FRAME_REPORT, EXPORTS,
 )

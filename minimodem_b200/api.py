@@ -20,6 +20,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libfsk_b200.so")
 MAX_BITS = 64
 FRAME_ACQUIRED = 0x80000000
+FRAME_REPORT = 0xFFFFFFFF
 
 
 class RxConfig(C.Structure):
@@ -60,12 +61,19 @@ FRAME_DTYPE = np.dtype([("bits_lo", "<u4"), ("bits_hi", "<u4"), ("confidence", "
 class StreamState(C.Structure):
     _fields_ = [("pos", C.c_uint64), ("nframes", C.c_uint32), ("carrier", C.c_uint32),
                 ("noconfidence", C.c_uint32), ("track_amplitude", C.c_float),
-                ("peak_confidence", C.c_float), ("done", C.c_uint32)]
+                ("peak_confidence", C.c_float), ("done", C.c_uint32),
+                ("carrier_nsamples", C.c_uint64), ("confidence_total", C.c_float),
+                ("amplitude_total", C.c_float), ("nframes_decoded", C.c_uint32),
+                ("reserved", C.c_uint32 * 3)]
 
 
 STATE_DTYPE = np.dtype([("pos", "<u8"), ("nframes", "<u4"), ("carrier", "<u4"),
                         ("noconfidence", "<u4"), ("track_amplitude", "<f4"),
-                        ("peak_confidence", "<f4"), ("done", "<u4")])
+                        ("peak_confidence", "<f4"), ("done", "<u4"),
+                        ("carrier_nsamples", "<u8"), ("confidence_total", "<f4"),
+                        ("amplitude_total", "<f4"), ("nframes_decoded", "<u4"),
+                        ("reserved", "<u4", (3,))])
+STATE_WORDS = STATE_DTYPE.itemsize // 4
 
 
 class TxConfig(C.Structure):
@@ -326,7 +334,7 @@ class RxEngine:
     def rx_batch(self, samples, nsamples=None, max_frames=None, frames=None, states=None,
                  nsamples_each=None, stream=None):
         """The rx loop over every row of `samples` ([nstreams, stride] float32 CUDA tensor).
-        Returns (frames [nstreams, max_frames, 5] int32, states [nstreams, 8] int32)."""
+        Returns (frames [nstreams, max_frames, 5] int32, states [nstreams, STATE_WORDS] int32)."""
         torch = _torch()
         assert samples.is_cuda and samples.dtype == torch.float32 and samples.is_contiguous()
         nstreams, stride = samples.shape
@@ -336,7 +344,7 @@ class RxEngine:
         if frames is None:
             frames = torch.empty((nstreams, max_frames, 5), dtype=torch.int32, device=samples.device)
         if states is None:
-            states = torch.zeros((nstreams, 8), dtype=torch.int32, device=samples.device)
+            states = torch.zeros((nstreams, STATE_WORDS), dtype=torch.int32, device=samples.device)
         rc = lib().fsk_b200_rx_batch(self._e, _ptr(samples), nstreams, stride, _ptr(nsamples_each), n_all,
                                      _ptr(frames), max_frames, _ptr(states), _stream_handle(stream))
         if rc:
@@ -347,7 +355,7 @@ class RxEngine:
         """Host arrays in, host records out (copies overlap demodulation inside the library).
         samples: [nstreams, stride] float32 numpy array or (pinned) CPU torch tensor;
         frames_out / states_out: optional preallocated host buffers ([n, max_frames, 5] and
-        [n, 8] int32 torch tensors, or numpy arrays of FRAME_DTYPE / STATE_DTYPE); states_out
+        [n, STATE_WORDS] int32 torch tensors, or numpy arrays of FRAME_DTYPE / STATE_DTYPE); states_out
         carries the per-stream state in and out (zero it for fresh streams)."""
         def hptr(t):
             return C.c_void_p(t.data_ptr()) if hasattr(t, "data_ptr") else t.ctypes.data_as(C.c_void_p)

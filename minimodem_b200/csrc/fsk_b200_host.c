@@ -304,10 +304,12 @@ int fsk_b200_rx_params_derive(const fsk_b200_rx_config *cfg, fsk_b200_rx_params 
 
 uint32_t fsk_b200_max_frames(const fsk_b200_rx_params *p, uint32_t nsamples)
 {
-    /* every recorded frame advances by at least frame_nsamples - overscan (:1407) */
+    /* every recorded frame advances by at least frame_nsamples - overscan (:1407);
+     * every session report is preceded by 21 no-confidence advances of try_max (:1295,:1318) */
     unsigned int min_adv = p->frame_nsamples > p->nsamples_overscan
 	? p->frame_nsamples - p->nsamples_overscan : 1;
-    return nsamples / min_adv + 2;
+    unsigned int drop_adv = 21u * (p->try_max_carrier ? p->try_max_carrier : 1u);
+    return nsamples / min_adv + nsamples / drop_adv + 4;
 }
 
 unsigned long long fsk_b200_frame_databits(const fsk_b200_rx_params *p, const fsk_b200_frame *f)

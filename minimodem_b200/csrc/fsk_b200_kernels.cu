@@ -118,8 +118,31 @@ __device__ __forceinline__ float frame_analyze(const Src &src, unsigned t0,
 	}
 	if (active && part == 0) {
 	    /* band_mag, src/fsk.c:107-114, then the decision at :158-169 */
-	    const float mag_mark = sqrtf(rm * rm + im * im) * geo.mag_scalar;
-	    const float mag_space = sqrtf(rs * rs + is * is) * geo.mag_scalar;
+	    float mag_mark = sqrtf(rm * rm + im * im) * geo.mag_scalar;
+	    float mag_space = sqrtf(rs * rs + is * is) * geo.mag_scalar;
+	    /* The reference drops off-tone magnitudes <= FLT_EPSILON from the noise sum
+	     * (src/fsk.c:279) so that exactly periodic tones give confidence = inf.  fp32
+	     * accumulation is good to ~2e-7 of the signal, not enough to classify a
+	     * magnitude that close to FLT_EPSILON: such (rare: synthetic, orthogonal-tone)
+	     * windows are re-summed in fp64, where float*float products are exact. */
+	    {
+		const float lo = fminf(mag_mark, mag_space), hi = fmaxf(mag_mark, mag_space);
+		if (lo < FSK_FLT_EPSILON + 2e-6f * hi) {
+		    const unsigned base = t0 + geo.bit_begin[w];
+		    double drm = 0., dim = 0., drs = 0., dis = 0.;
+		    for (unsigned n = 0; n < N; n++) {
+			const double x = (double)src(base + n);
+			const float4 c = tw[n];
+			drm = fma(x, (double)c.x, drm);
+			dim = fma(x, (double)c.y, dim);
+			drs = fma(x, (double)c.z, drs);
+			dis = fma(x, (double)c.w, dis);
+		    }
+		    const float frm = (float)drm, fim = (float)dim, frs = (float)drs, fis = (float)dis;
+		    mag_mark = sqrtf(frm * frm + fim * fim) * geo.mag_scalar;
+		    mag_space = sqrtf(frs * frs + fis * fis) * geo.mag_scalar;
+		}
+	    }
 	    const bool one = mag_mark > mag_space;		/* strict: tie -> space */
 	    const float sig = one ? mag_mark : mag_space;
 	    const float noise = one ? mag_space : mag_mark;
@@ -382,6 +405,9 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
 	unsigned nframes = st.nframes;
 	unsigned carrier = st.carrier, noconfidence = st.noconfidence;
 	float track_amplitude = st.track_amplitude, peak_confidence = st.peak_confidence;
+	unsigned long long carrier_nsamples = st.carrier_nsamples;
+	float confidence_total = st.confidence_total, amplitude_total = st.amplitude_total;
+	unsigned nframes_decoded = st.nframes_decoded;
 	unsigned done = 0;
 	unsigned filled = pos & ~3u;		/* ring holds [filled_lo, filled) */
 	__syncwarp(gmask);
@@ -442,14 +468,27 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
 	    if (confidence <= lc.confidence_threshold) {	/* :1292 */
 		if (++noconfidence > 20u) {			/* :1295 */
 		    if (carrier) {
-			carrier = 0;
-			track_amplitude = 0.f;			/* :1303-1308 */
+			/* report_no_carrier(), :1299-1302, as a record */
+			if (g == 0)
+			    store_frame(out + nframes, carrier_nsamples, confidence_total,
+				    amplitude_total, FSK_B200_FRAME_REPORT);
+			nframes++;
+			carrier = 0;				/* :1303-1308 */
+			carrier_nsamples = 0;
+			confidence_total = 0.f;
+			amplitude_total = 0.f;
+			nframes_decoded = 0;
+			track_amplitude = 0.f;
 		    }
 		}
 		advance = try_max;				/* :1318 */
 	    } else {
 		unsigned acquired = 0;
-		if (!carrier) {					/* :1332-1355 */
+		carrier_nsamples += lc.frame_nsamples;		/* :1324 */
+		if (carrier) {
+		    carrier_nsamples += frame_start;		/* :1329-1330: the COARSE start */
+		    carrier_nsamples -= lc.nsamples_overscan;
+		} else {					/* :1332-1355 */
 		    carrier = 1;
 		    acquired = FSK_B200_FRAME_ACQUIRED;
 		    want_refine = true;
@@ -476,6 +515,9 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
 		track_amplitude = (track_amplitude + amplitude) / 2.f;	/* :1391 */
 		if (peak_confidence < confidence)
 		    peak_confidence = confidence;
+		confidence_total += confidence;			/* :1397-1400 */
+		amplitude_total += amplitude;
+		nframes_decoded++;
 		noconfidence = 0;
 		if (g == 0)
 		    store_frame(out + nframes, bits, confidence, amplitude, frame_start | acquired);
@@ -495,6 +537,10 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
 	    st.noconfidence = noconfidence;
 	    st.track_amplitude = track_amplitude;
 	    st.peak_confidence = peak_confidence;
+	    st.carrier_nsamples = carrier_nsamples;
+	    st.confidence_total = confidence_total;
+	    st.amplitude_total = amplitude_total;
+	    st.nframes_decoded = nframes_decoded;
 	    st.done = done;
 	    states[s] = st;
 	}

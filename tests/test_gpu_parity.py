@@ -65,32 +65,41 @@ def rx_on_gpu(eng, streams, lanes=0):
 def as_oracle_frames(recs):
     out = []
     for r in recs:
-        bits = int(r["bits_lo"]) | (int(r["bits_hi"]) << 32)
         fs = int(r["frame_start"])
+        if fs == mm.FRAME_REPORT:
+            continue
+        bits = int(r["bits_lo"]) | (int(r["bits_hi"]) << 32)
         out.append((bits, np.float32(r["confidence"]), np.float32(r["amplitude"]), fs & 0x7FFFFFFF,
                     1 if fs & mm.FRAME_ACQUIRED else 0, 0))
     return out
 
 
-def reports_from(frames, mode, d, final_carrier):
-    """Recompute the NOCARRIER statistics from the frame records, in record order
-    (src/minimodem.c:1324-1330, :1397-1399, :253-291)."""
-    reps, cur = [], None
-    for fr in frames:
-        bits, conf, ampl, start, acquired, _ = fr
-        if acquired:
-            if cur is not None:
-                reps.append(cur)
-            cur = [0, 0, np.float32(0), np.float32(0)]
-            cur[1] += d.frame_nsamples
+def reports_of(recs, st_row):
+    """Carrier-session statistics exactly as the device accumulated them: the REPORT
+    records (carrier drops, src/minimodem.c:1298-1307) plus the session still open at
+    the end of the stream (:1469-1474), which lives in the stream state."""
+    reps, count, nfr = [], 0, 0
+    for r in recs:
+        fs = int(r["frame_start"])
+        if fs == mm.FRAME_REPORT:
+            reps.append((count, int(r["bits_lo"]) | (int(r["bits_hi"]) << 32), np.float32(r["confidence"]),
+                         np.float32(r["amplitude"]), nfr))
+            count = 0
         else:
-            cur[1] += d.frame_nsamples + start - d.nsamples_overscan
-        cur[0] += 1
-        cur[2] = np.float32(cur[2] + conf)
-        cur[3] = np.float32(cur[3] + ampl)
-    if cur is not None:     # printed at the drop (:1300) or at exit while carrier is up (:1469)
-        reps.append(cur)
-    return [(r[0], r[1], r[2], r[3], 0) for r in reps]
+            count = 1 if fs & mm.FRAME_ACQUIRED else count + 1
+            nfr += 1
+    if st_row["carrier"]:
+        assert int(st_row["nframes_decoded"]) == count
+        reps.append((count, int(st_row["carrier_nsamples"]), np.float32(st_row["confidence_total"]),
+                     np.float32(st_row["amplitude_total"]), nfr))
+    return reps
+
+
+def compare_reports(got, want, what=""):
+    assert len(got) == len(want), (what, got, want)
+    for a, b in zip(got, want):
+        assert a[0] == b[0] and a[1] == b[1] and a[4] == b[4], (what, a, b)
+        assert gu.close(a[2], b[2], cond=gu.CONF_COND) and gu.close(a[3], b[3]), (what, a, b)
 
 
 def compare_frames(got, want, what=""):
@@ -129,8 +138,8 @@ def test_rx_batch_on_reference_vectors(case):
                 frames = frames[:nacq[1]]
         assert orc.ref_decode(rx, frames) == bytes(g["stdout"])
     # stat line (the -P tests grep it for "confidence=inf ... (rate perfect)")
-    d = rx.derived()
-    reps = reports_from(got, rx, d, bool(st["carrier"][0]))
+    reps = reports_of(recs, st[0])
+    compare_reports(reps, want["reports"], case["name"])
     lines = [orc.report_line(rx, r) for r in reps]
     wantl = gu.stat_lines(g)
     if case["rx_one"]:
@@ -313,6 +322,10 @@ def test_roundtrip_property_large_batch(mode, kw, nstreams, nwords):
     if m.do_rx_sync:            # the sync byte itself is suppressed by the rx (:1436-1439)
         words[words == (m.sync_byte & 0xFF)] = 0x55
     lead = torch.randint(0, int(d.nsamples_per_bit), (nstreams,), generator=gen, dtype=torch.int32)
+    if m.do_rx_sync:
+        # without start/stop bits the reference can lock one bit off when silence precedes the
+        # periodic sync preamble (checked with the oracle); its own SAME test has no lead-in
+        lead.zero_()
     tcfg = mm.tx_config_from(cfg)
     n1 = int(orc.lib().orc_tx_nsamples(C.byref(m.tx_config(1.0, 4096, True)), nwords))
     nout = n1 + int(d.nsamples_per_bit) + 8
@@ -323,17 +336,24 @@ def test_roundtrip_property_large_batch(mode, kw, nstreams, nwords):
         frames, states = eng.rx_batch(x, nsamples=nout)
         torch.cuda.synchronize()
         results.append((frames.clone(), states.clone()))
-    assert torch.equal(results[0][1], results[1][1])
+    # the lane split changes only the order of the fp32 correlation sums: decisions and
+    # integers must agree exactly, float fields to tolerance
     fr = mm.frames_to_numpy(results[0][0])
     st = mm.states_to_numpy(results[0][1])
     fr1 = mm.frames_to_numpy(results[1][0])
+    st1 = mm.states_to_numpy(results[1][1])
     assert (st["done"] == 1).all()
+    for k in ("pos", "nframes", "carrier", "noconfidence", "done", "carrier_nsamples", "nframes_decoded"):
+        assert np.array_equal(st[k], st1[k]), k
+    assert np.allclose(st["confidence_total"], st1["confidence_total"], rtol=1e-4)
     w = words.numpy()
     shift = (1 if m.nstopbits != 0 else 0) + m.nstartbits
     mask = (1 << m.n_data_bits) - 1
     for s in range(nstreams):
         k = int(st["nframes"][s])
-        assert np.array_equal(fr[s, :k], fr1[s, :k]), s
+        for f in ("bits_lo", "bits_hi", "frame_start"):
+            assert np.array_equal(fr[s, :k][f], fr1[s, :k][f]), (s, f)
+        assert np.allclose(fr[s, :k]["confidence"], fr1[s, :k]["confidence"], rtol=1e-4)
         data = ((fr[s, :k]["bits_lo"].astype(np.uint64) | (fr[s, :k]["bits_hi"].astype(np.uint64) << np.uint64(32)))
                 >> np.uint64(shift)) & np.uint64(mask)
         if m.do_rx_sync:
