@@ -1,0 +1,424 @@
+/*
+ * fsk_b200_device.cuh -- device functions of the B200 FSK engine.
+ *
+ * Two implementations of the same arithmetic:
+ *
+ *  FAST   frame_analyze_fast<G,W,L> / find_frame_fast: the stream's samples are in a
+ *         per-stream shared-memory ring of R floats (R % 4 == 0); a window is read
+ *         through plain pointers (the one window of a frame that straddles the
+ *         ring end is split in two runs); each lane owns W windows and walks the
+ *         twiddle table once for all of them (n outer, windows inner): one
+ *         LDS.128 (twiddles) + W LDS.32 (samples) feed 4*W FMAs.  W, L are
+ *         compile-time so accumulators stay in registers.
+ *  GENERIC frame_analyze<G,Src> / find_frame: any source (ring with mask, or
+ *         global memory), run-time window split, fp64 folding for very long
+ *         windows.  Used when the windows do not fit shared memory (e.g. 0.5
+ *         baud) and as the reference implementation of the fast path in tests.
+ *
+ * All floating-point steps that decide anything follow the reference's order
+ * (src/fsk.c:107-174, :178-446, :449-538); comments carry its line numbers.
+ */
+#ifndef FSK_B200_DEVICE_CUH
+#define FSK_B200_DEVICE_CUH
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "fsk_b200_internal.h"
+
+#define FSK_FLT_EPSILON 1.1920928955078125e-07f
+#define ACC_BLOCK 64u		/* generic path: fp32 partial sums are folded into fp64 every ACC_BLOCK terms */
+#define FAST_MAX_N 2048u	/* fast path: plain fp32 accumulation up to this many terms per lane */
+
+/* ------------------------------------------------------------------------ */
+/* bit decision + bookkeeping shared by both paths                          */
+/* ------------------------------------------------------------------------ */
+
+/* band_mag (src/fsk.c:107-114) for both tones, the decision (:158-169) and the
+ * pass-1 check (:211); the result goes to the per-stream scratch: x = signal
+ * magnitude, y = noise magnitude with the bit value in its sign. */
+__device__ __forceinline__ bool decide_bit(float mag_mark, float mag_space, unsigned expect,
+	float2 *slot)
+{
+    const bool one = mag_mark > mag_space;			/* strict: tie -> space */
+    const float sig = one ? mag_mark : mag_space;
+    const float noise = one ? mag_space : mag_mark;
+    *slot = make_float2(sig, one ? -noise : noise);
+    return expect != 2u && expect != (one ? 1u : 0u);
+}
+
+/* The reference drops off-tone magnitudes <= FLT_EPSILON from the noise sum
+ * (src/fsk.c:279) so that exactly periodic tones give confidence = inf.  fp32
+ * accumulation is good to ~2e-7 of the signal, not enough to classify a magnitude
+ * that close to FLT_EPSILON: such (rare: synthetic, orthogonal-tone) windows are
+ * re-summed in fp64, where float*float products are exact. */
+__device__ __forceinline__ bool needs_resum(float mag_mark, float mag_space)
+{
+    const float lo = fminf(mag_mark, mag_space), hi = fmaxf(mag_mark, mag_space);
+    return lo < FSK_FLT_EPSILON + 2e-6f * hi;
+}
+
+/* src/fsk.c:271-342 over the scratch of one candidate, bit index ascending, one
+ * rounding per operation.  `owner(w)` tells whether this lane computes the
+ * divergence term of window w.  All lanes of the group execute this and end up
+ * with the same values. */
+template <class ForOwn>
+__device__ __forceinline__ float confidence_from_scratch(float2 *scr, unsigned nb, unsigned gmask,
+	ForOwn for_own_windows, unsigned long long &bits_out, float &ampl_out)
+{
+    float total_sig = 0.f, total_noise = 0.f, avg_mark = 0.f, avg_space = 0.f;
+    unsigned n_mark = 0;
+    unsigned bits_lo = 0, bits_hi = 0;
+    for (unsigned b = 0; b < nb; b++) {
+	const float2 v = scr[b];
+	const float noise = fabsf(v.y);
+	const unsigned one = __float_as_uint(v.y) >> 31;	/* the bit value rides in the sign */
+	total_sig += v.x;
+	if (noise > FSK_FLT_EPSILON)				/* :279 */
+	    total_noise += noise;
+	avg_mark += one ? v.x : 0.f;		/* x + 0 is exact: same value as the reference's branch */
+	avg_space += one ? 0.f : v.x;
+	n_mark += one;
+	const unsigned m = one << (b & 31u);
+	bits_lo |= b < 32u ? m : 0u;
+	bits_hi |= b < 32u ? 0u : m;
+    }
+    const unsigned n_space = nb - n_mark;
+    const float snr = total_sig / total_noise;			/* :292, may be +inf */
+    const float avg_bit_sig = total_sig / (float)(int)nb;	/* :295 */
+    if (n_mark)
+	avg_mark = avg_mark / (float)n_mark;			/* :298-301 */
+    if (n_space)
+	avg_space = avg_space / (float)n_space;
+
+    /* divergence terms (:305-311): one division per bit, done by the window owners ... */
+    __syncwarp(gmask);
+    for_own_windows([&](unsigned w) {
+	const float2 v = scr[w];
+	const float other = (__float_as_uint(v.y) >> 31) ? avg_mark : avg_space;
+	scr[w].x = fabsf(v.x - other) / other;
+    });
+    __syncwarp(gmask);
+    /* ... and summed in bit order */
+    float divergence = 0.f;
+    for (unsigned b = 0; b < nb; b++)
+	divergence += scr[b].x;
+    divergence *= 2.f;						/* :312-313 */
+    divergence = divergence / (float)(int)nb;
+
+    bits_out = ((unsigned long long)bits_hi << 32) | bits_lo;
+    ampl_out = avg_bit_sig;					/* :342 */
+    return snr * (1.0f - divergence);				/* :336 */
+}
+
+/* ======================================================================== */
+/* GENERIC path                                                             */
+/* ======================================================================== */
+
+/* shared-memory ring addressed by absolute sample index (power-of-two size) */
+struct RingSrc {
+    const float *ring;
+    unsigned mask;
+    __device__ __forceinline__ float operator()(unsigned i) const { return ring[i & mask]; }
+};
+
+/* straight from global memory, zero beyond the valid length */
+struct GlobalSrc {
+    const float *x;
+    unsigned n;
+    __device__ __forceinline__ float operator()(unsigned i) const { return i < n ? __ldg(x + i) : 0.0f; }
+};
+
+template <class Src>
+__device__ __forceinline__ void resum_fp64(const Src &src, unsigned base, unsigned N,
+	const float4 *__restrict__ tw, float mag_scalar, float &mag_mark, float &mag_space)
+{
+    double drm = 0., dim = 0., drs = 0., dis = 0.;
+    for (unsigned n = 0; n < N; n++) {
+	const double x = (double)src(base + n);
+	const float4 c = tw[n];
+	drm = fma(x, (double)c.x, drm);
+	dim = fma(x, (double)c.y, dim);
+	drs = fma(x, (double)c.z, drs);
+	dis = fma(x, (double)c.w, dis);
+    }
+    const float frm = (float)drm, fim = (float)dim, frs = (float)drs, fis = (float)dis;
+    mag_mark = sqrtf(frm * frm + fim * fim) * mag_scalar;
+    mag_space = sqrtf(frs * frs + fis * fis) * mag_scalar;
+}
+
+template <int G, class Src>
+__device__ __noinline__ float frame_analyze(const Src &src, unsigned t0,
+	const fsk_b200_geom &geo, int sel, const float4 *__restrict__ tw, float2 *scr,
+	unsigned g, unsigned gmask, unsigned long long &bits_out, float &ampl_out)
+{
+    const unsigned N = geo.bit_nsamples, nb = geo.n_bits, L = geo.lanes_per_window;
+    const unsigned wpp = G / L;			/* windows analysed per pass */
+    const unsigned part = g & (L - 1), wslot = g / L;
+    bool mismatch = false;
+
+    __syncwarp(gmask);				/* previous readers of scr are done */
+    for (unsigned w0 = 0; w0 < nb; w0 += wpp) {
+	const unsigned w = w0 + wslot;
+	const bool active = w < nb;
+	float rm = 0.f, im = 0.f, rs = 0.f, is = 0.f;
+	if (active) {
+	    const unsigned base = t0 + geo.bit_begin[w];
+	    /* bounded fp32 partial sums folded into fp64 (very long windows stay accurate) */
+	    double drm = 0., dim = 0., drs = 0., dis = 0.;
+	    for (unsigned n0 = part; n0 < N; n0 += ACC_BLOCK * L) {
+		const unsigned nend = min(N, n0 + ACC_BLOCK * L);
+		float prm = 0.f, pim = 0.f, prs = 0.f, pis = 0.f;
+		for (unsigned n = n0; n < nend; n += L) {
+		    const float x = src(base + n);
+		    const float4 c = tw[n];
+		    prm = fmaf(x, c.x, prm);
+		    pim = fmaf(x, c.y, pim);
+		    prs = fmaf(x, c.z, prs);
+		    pis = fmaf(x, c.w, pis);
+		}
+		drm += prm; dim += pim; drs += prs; dis += pis;
+	    }
+	    rm = (float)drm; im = (float)dim; rs = (float)drs; is = (float)dis;
+	}
+	for (unsigned o = L >> 1; o; o >>= 1) {
+	    rm += __shfl_xor_sync(gmask, rm, o);
+	    im += __shfl_xor_sync(gmask, im, o);
+	    rs += __shfl_xor_sync(gmask, rs, o);
+	    is += __shfl_xor_sync(gmask, is, o);
+	}
+	if (active && part == 0) {
+	    float mag_mark = sqrtf(rm * rm + im * im) * geo.mag_scalar;
+	    float mag_space = sqrtf(rs * rs + is * is) * geo.mag_scalar;
+	    if (needs_resum(mag_mark, mag_space))
+		resum_fp64(src, t0 + geo.bit_begin[w], N, tw, geo.mag_scalar, mag_mark, mag_space);
+	    mismatch |= decide_bit(mag_mark, mag_space, geo.expect[sel][w], scr + w);
+	}
+    }
+    __syncwarp(gmask);
+    if (__any_sync(gmask, mismatch)) {		/* pass 1 reject, src/fsk.c:211-212 */
+	bits_out = 0;
+	ampl_out = 0.f;
+	return 0.f;
+    }
+    return confidence_from_scratch(scr, nb, gmask, [&](auto body) {
+	if (part == 0)
+	    for (unsigned w = wslot; w < nb; w += wpp)
+		body(w);
+    }, bits_out, ampl_out);
+}
+
+/* frame search: src/fsk.c:449-538 */
+template <class Analyze>
+__device__ __forceinline__ float search_frames(Analyze analyze, unsigned try_first, unsigned try_max,
+	unsigned try_step, float limit, unsigned long long &best_bits, float &best_a, unsigned &best_t)
+{
+    float best_c = 0.f;
+    best_t = 0;
+    best_a = 0.f;
+    best_bits = 0;
+    for (int j = 0;; j++) {					/* :477-502 */
+	const int up = (j & 1) ? 1 : -1;
+	const int t = (int)try_first + up * ((j + 1) / 2) * (int)try_step;
+	if (t >= (int)try_max)
+	    break;
+	if (t < 0)
+	    continue;
+	unsigned long long bits;
+	float a;
+	const float c = analyze((unsigned)t, bits, a);
+	if (best_c < c) {			/* NaN and negatives never win */
+	    best_t = (unsigned)t;
+	    best_c = c;
+	    best_a = a;
+	    best_bits = bits;
+	    if (best_c >= limit)
+		break;				/* first to reach the limit wins */
+	}
+    }
+    return best_c;
+}
+
+template <int G, class Src>
+__device__ __forceinline__ float find_frame(const Src &src, unsigned base,
+	const fsk_b200_geom &geo, int sel, const float4 *__restrict__ tw, float2 *scr,
+	unsigned g, unsigned gmask, unsigned try_first, unsigned try_max, unsigned try_step,
+	float limit, unsigned long long &best_bits, float &best_a, unsigned &best_t)
+{
+    return search_frames([&](unsigned t, unsigned long long &bits, float &a) {
+	return frame_analyze<G, Src>(src, base + t, geo, sel, tw, scr, g, gmask, bits, a);
+    }, try_first, try_max, try_step, limit, best_bits, best_a, best_t);
+}
+
+/* ======================================================================== */
+/* FAST path                                                                */
+/* ======================================================================== */
+
+/* A per-stream ring of R floats (R % 4 == 0) followed by a MIRROR of its first
+ * `pad` floats (pad >= bit_nsamples - 1, pad % 4 == 0): ring[R + k] == ring[k].
+ * A bit window that starts anywhere in [0, R) is therefore one linear run, no
+ * wrap handling inside the correlation loop.  `pos_off` is the ring offset of the
+ * absolute sample index `pos` (pos_off == pos mod 4 is kept, so the 16-byte
+ * chunks of the stream line up with 16-byte chunks of the ring). */
+struct Ring {
+    float *ring;
+    unsigned R, pad;
+};
+
+__device__ __forceinline__ unsigned ring_wrap(unsigned off, unsigned R) { return off >= R ? off - R : off; }
+
+template <int G, int W, int L>
+__device__ __forceinline__ float frame_analyze_fast(const Ring rg, unsigned cand_off,
+	const fsk_b200_geom &geo, int sel, const float4 *__restrict__ tw, float2 *scr,
+	unsigned g, unsigned gmask, unsigned long long &bits_out, float &ampl_out)
+{
+    /* cand_off: ring offset (< R) of the candidate's first sample */
+    constexpr unsigned WPP = G / L;		/* windows per pass */
+    const unsigned N = geo.bit_nsamples, nb = geo.n_bits, R = rg.R;
+    const unsigned part = g % L, wslot = g / L;
+
+    /* this lane's windows: w = j*WPP + wslot (slots past n_bits read window 0: harmless) */
+    const float *p[W];
+#pragma unroll
+    for (int j = 0; j < W; j++) {
+	const unsigned w = j * WPP + wslot;
+	p[j] = rg.ring + ring_wrap(cand_off + (w < nb ? geo.bit_begin[w] : 0u), R);
+    }
+
+    float acc[W][4];
+#pragma unroll
+    for (int j = 0; j < W; j++)
+	acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+
+    __syncwarp(gmask);				/* previous readers of scr are done */
+#pragma unroll 4
+    for (unsigned n = part; n < N; n += L) {
+	const float4 c = tw[n];
+#pragma unroll
+	for (int j = 0; j < W; j++) {
+	    const float x = p[j][n];
+	    acc[j][0] = fmaf(x, c.x, acc[j][0]);
+	    acc[j][1] = fmaf(x, c.y, acc[j][1]);
+	    acc[j][2] = fmaf(x, c.z, acc[j][2]);
+	    acc[j][3] = fmaf(x, c.w, acc[j][3]);
+	}
+    }
+
+    if (L > 1) {
+#pragma unroll
+	for (int o = L >> 1; o; o >>= 1) {
+#pragma unroll
+	    for (int k = 0; k < 4; k++)
+		acc[0][k] += __shfl_xor_sync(gmask, acc[0][k], o);
+	}
+    }
+
+    bool mismatch = false;
+#pragma unroll
+    for (int j = 0; j < W; j++) {
+	const unsigned w = j * WPP + wslot;
+	if (w < nb && part == 0) {
+	    float mag_mark = sqrtf(acc[j][0] * acc[j][0] + acc[j][1] * acc[j][1]) * geo.mag_scalar;
+	    float mag_space = sqrtf(acc[j][2] * acc[j][2] + acc[j][3] * acc[j][3]) * geo.mag_scalar;
+	    if (needs_resum(mag_mark, mag_space)) {
+		const float *q = p[j];
+		double drm = 0., dim = 0., drs = 0., dis = 0.;
+		for (unsigned i = 0; i < N; i++) {
+		    const double x = (double)q[i];
+		    const float4 c = tw[i];
+		    drm = fma(x, (double)c.x, drm);
+		    dim = fma(x, (double)c.y, dim);
+		    drs = fma(x, (double)c.z, drs);
+		    dis = fma(x, (double)c.w, dis);
+		}
+		const float frm = (float)drm, fim = (float)dim, frs = (float)drs, fis = (float)dis;
+		mag_mark = sqrtf(frm * frm + fim * fim) * geo.mag_scalar;
+		mag_space = sqrtf(frs * frs + fis * fis) * geo.mag_scalar;
+	    }
+	    mismatch |= decide_bit(mag_mark, mag_space, geo.expect[sel][w], scr + w);
+	}
+    }
+    __syncwarp(gmask);
+    if (__any_sync(gmask, mismatch)) {		/* pass 1 reject, src/fsk.c:211-212 */
+	bits_out = 0;
+	ampl_out = 0.f;
+	return 0.f;
+    }
+    return confidence_from_scratch(scr, nb, gmask, [&](auto body) {
+	if (part == 0) {
+#pragma unroll
+	    for (int j = 0; j < W; j++) {
+		const unsigned w = j * WPP + wslot;
+		if (w < nb)
+		    body(w);
+	    }
+	}
+    }, bits_out, ampl_out);
+}
+
+template <int G, int W, int L>
+__device__ __forceinline__ float find_frame_fast(const Ring rg, unsigned pos_off,
+	const fsk_b200_geom &geo, int sel, const float4 *__restrict__ tw, float2 *scr,
+	unsigned g, unsigned gmask, unsigned try_first, unsigned try_max, unsigned try_step,
+	float limit, unsigned long long &best_bits, float &best_a, unsigned &best_t)
+{
+    return search_frames([&](unsigned t, unsigned long long &bits, float &a) {
+	return frame_analyze_fast<G, W, L>(rg, ring_wrap(pos_off + t, rg.R), geo, sel, tw, scr,
+		g, gmask, bits, a);
+    }, try_first, try_max, try_step, limit, best_bits, best_a, best_t);
+}
+
+/* ------------------------------------------------------------------------ */
+/* asynchronous ring fill: HBM -> shared memory, 16 bytes per cp.async,     */
+/* every sample fetched once; bytes at or past the valid length arrive as 0 */
+/* ------------------------------------------------------------------------ */
+
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int NKEEP>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" :: "n"(NKEEP) : "memory"); }
+
+/* copies absolute indices [from, to) (multiples of 4) of stream x (valid length n)
+ * into the ring and its mirror; `pos`/`pos_off` anchor the mapping
+ * (to - (pos & ~3) <= R). */
+template <int G>
+__device__ __forceinline__ void ring_issue(const Ring rg, const float *__restrict__ x, unsigned n,
+	unsigned pos, unsigned pos_off, unsigned from, unsigned to, unsigned g)
+{
+    unsigned i = from + 4u * g;
+    if (i >= to)
+	return;
+    /* ring offset of absolute index i: pos_off + (i - pos), i - pos >= -3 */
+    int off0 = (int)pos_off + (int)(i - pos);
+    if (off0 < 0)
+	off0 += (int)rg.R;
+    unsigned off = (unsigned)off0;
+    if (off >= rg.R)
+	off -= rg.R;
+    const unsigned ring_s = (unsigned)__cvta_generic_to_shared(rg.ring);
+    const float *src = x + i;
+    for (; i < to; i += 4u * G, src += 4 * G) {
+	const unsigned valid = i + 4u <= n ? 16u : (i < n ? (n - i) * 4u : 0u);
+	const float *s = valid ? src : x;
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n"
+		:: "r"(ring_s + off * 4u), "l"(s), "r"(valid) : "memory");
+	if (off < rg.pad)
+	    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n"
+		    :: "r"(ring_s + (rg.R + off) * 4u), "l"(s), "r"(valid) : "memory");
+	off += 4u * G;
+	if (off >= rg.R)
+	    off -= rg.R;
+    }
+}
+
+__device__ __forceinline__ void store_frame(fsk_b200_frame *f, unsigned long long bits, float conf,
+	float ampl, unsigned start)
+{
+    uint32_t *p = reinterpret_cast<uint32_t *>(f);
+    p[0] = (uint32_t)bits;
+    p[1] = (uint32_t)(bits >> 32);
+    p[2] = __float_as_uint(conf);
+    p[3] = __float_as_uint(ampl);
+    p[4] = start;
+}
+
+#endif /* FSK_B200_DEVICE_CUH */

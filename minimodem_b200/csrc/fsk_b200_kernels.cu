@@ -31,256 +31,18 @@
 #include <string.h>
 
 #include "fsk_b200_internal.h"
-
-#define FSK_FLT_EPSILON 1.1920928955078125e-07f
-#define ACC_BLOCK 64u	/* fp32 partial sums are folded into fp64 every ACC_BLOCK terms */
+#include "fsk_b200_device.cuh"
 
 static unsigned long long g_launches;
 
 #define CUDA_TRY(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
     fsk_b200_set_error("%s: %s", #call, cudaGetErrorString(e_)); return -EIO; } } while (0)
 
-/* ------------------------------------------------------------------------ */
-/* sample sources                                                           */
-/* ------------------------------------------------------------------------ */
-
-/* shared-memory ring addressed by absolute sample index */
-struct RingSrc {
-    const float *ring;
-    unsigned mask;
-    __device__ __forceinline__ float operator()(unsigned i) const { return ring[i & mask]; }
-};
-
-/* straight from global memory, zero beyond the valid length (windows that do
- * not fit the ring: very low baud rates) */
-struct GlobalSrc {
-    const float *x;
-    unsigned n;
-    __device__ __forceinline__ float operator()(unsigned i) const { return i < n ? __ldg(x + i) : 0.0f; }
-};
 
 /* ------------------------------------------------------------------------ */
-/* frame analysis: src/fsk.c:178-446 for one candidate start                */
+/* shared memory carve-up                                                   */
 /* ------------------------------------------------------------------------ */
-
-template <int G, class Src>
-__device__ __forceinline__ float frame_analyze(const Src &src, unsigned t0,
-	const fsk_b200_geom &geo, int sel, const float4 *__restrict__ tw, float2 *scr,
-	unsigned g, unsigned gmask, unsigned long long &bits_out, float &ampl_out)
-{
-    const unsigned N = geo.bit_nsamples, nb = geo.n_bits, L = geo.lanes_per_window;
-    const unsigned wpp = G / L;			/* windows analysed per pass */
-    const unsigned part = g & (L - 1), wslot = g / L;
-    bool mismatch = false;
-
-    __syncwarp(gmask);				/* previous readers of scr are done */
-    for (unsigned w0 = 0; w0 < nb; w0 += wpp) {
-	const unsigned w = w0 + wslot;
-	const bool active = w < nb;
-	float rm = 0.f, im = 0.f, rs = 0.f, is = 0.f;
-	if (active) {
-	    const unsigned base = t0 + geo.bit_begin[w];
-	    if (N <= ACC_BLOCK * L) {
-#pragma unroll 4
-		for (unsigned n = part; n < N; n += L) {
-		    const float x = src(base + n);
-		    const float4 c = tw[n];
-		    rm = fmaf(x, c.x, rm);
-		    im = fmaf(x, c.y, im);
-		    rs = fmaf(x, c.z, rs);
-		    is = fmaf(x, c.w, is);
-		}
-	    } else {
-		/* long windows: bounded fp32 partial sums folded into fp64 */
-		double drm = 0., dim = 0., drs = 0., dis = 0.;
-		for (unsigned n0 = part; n0 < N; n0 += ACC_BLOCK * L) {
-		    const unsigned nend = min(N, n0 + ACC_BLOCK * L);
-		    float prm = 0.f, pim = 0.f, prs = 0.f, pis = 0.f;
-#pragma unroll 4
-		    for (unsigned n = n0; n < nend; n += L) {
-			const float x = src(base + n);
-			const float4 c = tw[n];
-			prm = fmaf(x, c.x, prm);
-			pim = fmaf(x, c.y, pim);
-			prs = fmaf(x, c.z, prs);
-			pis = fmaf(x, c.w, pis);
-		    }
-		    drm += prm; dim += pim; drs += prs; dis += pis;
-		}
-		rm = (float)drm; im = (float)dim; rs = (float)drs; is = (float)dis;
-	    }
-	}
-	for (unsigned o = L >> 1; o; o >>= 1) {
-	    rm += __shfl_xor_sync(gmask, rm, o);
-	    im += __shfl_xor_sync(gmask, im, o);
-	    rs += __shfl_xor_sync(gmask, rs, o);
-	    is += __shfl_xor_sync(gmask, is, o);
-	}
-	if (active && part == 0) {
-	    /* band_mag, src/fsk.c:107-114, then the decision at :158-169 */
-	    float mag_mark = sqrtf(rm * rm + im * im) * geo.mag_scalar;
-	    float mag_space = sqrtf(rs * rs + is * is) * geo.mag_scalar;
-	    /* The reference drops off-tone magnitudes <= FLT_EPSILON from the noise sum
-	     * (src/fsk.c:279) so that exactly periodic tones give confidence = inf.  fp32
-	     * accumulation is good to ~2e-7 of the signal, not enough to classify a
-	     * magnitude that close to FLT_EPSILON: such (rare: synthetic, orthogonal-tone)
-	     * windows are re-summed in fp64, where float*float products are exact. */
-	    {
-		const float lo = fminf(mag_mark, mag_space), hi = fmaxf(mag_mark, mag_space);
-		if (lo < FSK_FLT_EPSILON + 2e-6f * hi) {
-		    const unsigned base = t0 + geo.bit_begin[w];
-		    double drm = 0., dim = 0., drs = 0., dis = 0.;
-		    for (unsigned n = 0; n < N; n++) {
-			const double x = (double)src(base + n);
-			const float4 c = tw[n];
-			drm = fma(x, (double)c.x, drm);
-			dim = fma(x, (double)c.y, dim);
-			drs = fma(x, (double)c.z, drs);
-			dis = fma(x, (double)c.w, dis);
-		    }
-		    const float frm = (float)drm, fim = (float)dim, frs = (float)drs, fis = (float)dis;
-		    mag_mark = sqrtf(frm * frm + fim * fim) * geo.mag_scalar;
-		    mag_space = sqrtf(frs * frs + fis * fis) * geo.mag_scalar;
-		}
-	    }
-	    const bool one = mag_mark > mag_space;		/* strict: tie -> space */
-	    const float sig = one ? mag_mark : mag_space;
-	    const float noise = one ? mag_space : mag_mark;
-	    /* the bit value rides in the sign of the (non-negative) noise magnitude */
-	    scr[w] = make_float2(sig, one ? -noise : noise);
-	    const unsigned e = geo.expect[sel][w];
-	    if (e != 2u && e != (one ? 1u : 0u))
-		mismatch = true;			/* pass 1 reject, src/fsk.c:211-212 */
-	}
-    }
-    __syncwarp(gmask);
-    if (__any_sync(gmask, mismatch)) {
-	bits_out = 0;
-	ampl_out = 0.f;
-	return 0.f;
-    }
-
-    /* src/fsk.c:271-301, bit index ascending, one rounding per operation */
-    float total_sig = 0.f, total_noise = 0.f, avg_mark = 0.f, avg_space = 0.f;
-    unsigned n_mark = 0, n_space = 0;
-    unsigned long long bits = 0;
-    for (unsigned b = 0; b < nb; b++) {
-	const float2 v = scr[b];
-	const float noise = fabsf(v.y);
-	total_sig += v.x;
-	if (noise > FSK_FLT_EPSILON)
-	    total_noise += noise;
-	if (signbit(v.y)) {
-	    avg_mark += v.x;
-	    n_mark++;
-	    bits |= 1ull << b;
-	} else {
-	    avg_space += v.x;
-	    n_space++;
-	}
-    }
-    const float snr = total_sig / total_noise;		/* may be +inf */
-    const float avg_bit_sig = total_sig / (float)(int)nb;
-    if (n_mark)
-	avg_mark = avg_mark / (float)n_mark;
-    if (n_space)
-	avg_space = avg_space / (float)n_space;
-
-    /* divergence terms (src/fsk.c:305-311) computed by the window owners ... */
-    __syncwarp(gmask);
-    for (unsigned w0 = 0; w0 < nb; w0 += wpp) {
-	const unsigned w = w0 + wslot;
-	if (w < nb && part == 0) {
-	    const float2 v = scr[w];
-	    const float other = signbit(v.y) ? avg_mark : avg_space;
-	    scr[w].x = fabsf(v.x - other) / other;
-	}
-    }
-    __syncwarp(gmask);
-    /* ... and summed in bit order */
-    float divergence = 0.f;
-    for (unsigned b = 0; b < nb; b++)
-	divergence += scr[b].x;
-    divergence *= 2.f;
-    divergence = divergence / (float)(int)nb;
-
-    bits_out = bits;
-    ampl_out = avg_bit_sig;
-    return snr * (1.0f - divergence);			/* src/fsk.c:336 */
-}
-
-/* ------------------------------------------------------------------------ */
-/* frame search: src/fsk.c:449-538                                          */
-/* ------------------------------------------------------------------------ */
-
-template <int G, class Src>
-__device__ __forceinline__ float find_frame(const Src &src, unsigned base,
-	const fsk_b200_geom &geo, int sel, const float4 *__restrict__ tw, float2 *scr,
-	unsigned g, unsigned gmask, unsigned try_first, unsigned try_max, unsigned try_step,
-	float limit, unsigned long long &best_bits, float &best_a, unsigned &best_t)
-{
-    float best_c = 0.f;
-    best_t = 0;
-    best_a = 0.f;
-    best_bits = 0;
-    for (int j = 0;; j++) {
-	const int up = (j & 1) ? 1 : -1;
-	const int t = (int)try_first + up * ((j + 1) / 2) * (int)try_step;
-	if (t >= (int)try_max)
-	    break;
-	if (t < 0)
-	    continue;
-	unsigned long long bits;
-	float a;
-	const float c = frame_analyze<G, Src>(src, base + (unsigned)t, geo, sel, tw, scr, g, gmask,
-		bits, a);
-	if (best_c < c) {			/* NaN and negatives never win */
-	    best_t = (unsigned)t;
-	    best_c = c;
-	    best_a = a;
-	    best_bits = bits;
-	    if (best_c >= limit)
-		break;				/* first to reach the limit wins */
-	}
-    }
-    return best_c;
-}
-
-/* ------------------------------------------------------------------------ */
-/* ring fill: HBM -> shared memory, 16 bytes per lane, each sample once     */
-/* ------------------------------------------------------------------------ */
-
-template <int G>
-__device__ __forceinline__ void ring_fill(float *ring, unsigned mask, const float *__restrict__ x,
-	unsigned n, unsigned from, unsigned to, unsigned g)
-{
-    /* from, to multiples of 4; x 16-byte aligned */
-    for (unsigned i = from + 4u * g; i < to; i += 4u * G) {
-	float4 v;
-	if (i + 4u <= n) {
-	    v = __ldg(reinterpret_cast<const float4 *>(x + i));
-	} else {
-	    v.x = (i + 0u < n) ? __ldg(x + i + 0) : 0.f;
-	    v.y = (i + 1u < n) ? __ldg(x + i + 1) : 0.f;
-	    v.z = (i + 2u < n) ? __ldg(x + i + 2) : 0.f;
-	    v.w = (i + 3u < n) ? __ldg(x + i + 3) : 0.f;
-	}
-	*reinterpret_cast<float4 *>(ring + (i & mask)) = v;
-    }
-}
-
-__device__ __forceinline__ void store_frame(fsk_b200_frame *f, unsigned long long bits, float conf,
-	float ampl, unsigned start)
-{
-    uint32_t *p = reinterpret_cast<uint32_t *>(f);
-    p[0] = (uint32_t)bits;
-    p[1] = (uint32_t)(bits >> 32);
-    p[2] = __float_as_uint(conf);
-    p[3] = __float_as_uint(ampl);
-    p[4] = start;
-}
-
-/* shared memory carve-up common to both kernels */
+/* [twiddles: N float4 (optional)] [rings: slots x (ring_floats + pad)] [scratch: slots x n_bits float2] */
 struct Smem {
     const float4 *tw;
     float *ring;
@@ -289,10 +51,9 @@ struct Smem {
 
 template <int G>
 __device__ __forceinline__ Smem carve(float4 *smem, const fsk_b200_geom &geo,
-	const float4 *__restrict__ tw_global, unsigned tw_in_smem, unsigned ring_floats,
-	unsigned warps_per_block)
+	const float4 *__restrict__ tw_global, unsigned tw_in_smem, unsigned ring_floats)
 {
-    const unsigned N = geo.bit_nsamples;
+    const unsigned N = geo.bit_nsamples, wpb = blockDim.x >> 5;
     Smem s;
     float4 *p = smem;
     if (tw_in_smem) {
@@ -304,70 +65,91 @@ __device__ __forceinline__ Smem carve(float4 *smem, const fsk_b200_geom &geo,
 	s.tw = tw_global;
     }
     const unsigned spw = 32 / G;
-    const unsigned warp = threadIdx.x >> 5, sidx = (threadIdx.x & 31) / G;
-    const unsigned slot = warp * spw + sidx;
+    const unsigned slot = (threadIdx.x >> 5) * spw + (threadIdx.x & 31) / G;
     float *rings = reinterpret_cast<float *>(p);
-    s.ring = rings + (size_t)slot * ring_floats;
-    float2 *scrs = reinterpret_cast<float2 *>(rings + (size_t)warps_per_block * spw * ring_floats);
+    const unsigned pad = ring_floats ? ((geo.bit_nsamples + 3u) & ~3u) : 0u;
+    s.ring = rings + (size_t)slot * (ring_floats + pad);
+    float2 *scrs = reinterpret_cast<float2 *>(rings + (size_t)wpb * spw * (ring_floats + pad));
     s.scr = scrs + (size_t)slot * geo.n_bits;
     __syncthreads();
     return s;
 }
 
+#define GROUP_VARS \
+    const unsigned lane = threadIdx.x & 31, g = lane % G, sidx = lane / G, spw = 32 / G; \
+    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (sidx * G)); \
+    const unsigned wpb = blockDim.x >> 5, warp = threadIdx.x >> 5; \
+    (void)lane
+
+/* per-call arguments of the batched search */
+struct FindArgs {
+    const float *samples;
+    unsigned nstreams;
+    size_t stride;
+    const uint32_t *offset, *nvalid, *try_first, *try_max, *try_step;
+    const float *limit;
+    const uint8_t *expect_sel;
+    fsk_b200_frame *frames;
+};
+
+struct RxArgs {
+    const float *samples;
+    unsigned nstreams;
+    size_t stride;
+    const uint32_t *nsamples;
+    uint32_t nsamples_all;
+    fsk_b200_frame *frames;
+    uint32_t max_frames;
+    fsk_b200_stream_state *states;
+};
+
 /* ------------------------------------------------------------------------ */
-/* K1: batched fsk_find_frame                                               */
+/* K1: batched fsk_find_frame (src/fsk.c:449-538), one search per stream     */
 /* ------------------------------------------------------------------------ */
 
-template <int G>
+/* MODE 0: fast (ring + compile-time split), 1: generic from global memory */
+template <int G, int W, int L, int MODE>
 __global__ void __launch_bounds__(256)
 k_find_frame(const __grid_constant__ fsk_b200_geom geo, const float4 *__restrict__ tw_global,
-	unsigned tw_in_smem, unsigned ring_floats, const float *__restrict__ samples,
-	unsigned nstreams, size_t stride, const uint32_t *__restrict__ offset,
-	const uint32_t *__restrict__ nvalid, const uint32_t *__restrict__ try_first,
-	const uint32_t *__restrict__ try_max, const uint32_t *__restrict__ try_step,
-	const float *__restrict__ limit, const uint8_t *__restrict__ expect_sel,
-	fsk_b200_frame *__restrict__ frames)
+	unsigned tw_in_smem, unsigned ring_floats, const __grid_constant__ FindArgs a)
 {
     extern __shared__ float4 smem4[];
-    const unsigned wpb = blockDim.x >> 5;
-    const Smem sm = carve<G>(smem4, geo, tw_global, tw_in_smem, ring_floats, wpb);
-    const unsigned lane = threadIdx.x & 31, g = lane % G, sidx = lane / G, spw = 32 / G;
-    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (sidx * G));
-    const unsigned warp = threadIdx.x >> 5;
-    const unsigned mask = ring_floats ? ring_floats - 1u : 0u;
+    const Smem sm = carve<G>(smem4, geo, tw_global, tw_in_smem, ring_floats);
+    GROUP_VARS;
+    const Ring rg = { sm.ring, ring_floats, (geo.bit_nsamples + 3u) & ~3u };
 
-    for (unsigned s = (blockIdx.x * wpb + warp) * spw + sidx; s < nstreams;
+    for (unsigned s = (blockIdx.x * wpb + warp) * spw + sidx; s < a.nstreams;
 	    s += gridDim.x * wpb * spw) {
-	const float *x = samples + (size_t)s * stride;
-	const unsigned off = offset ? offset[s] : 0u;
-	const unsigned n = nvalid[s];
-	const unsigned tmax = try_max[s];
-	unsigned tstep = try_step[s];
+	const float *x = a.samples + (size_t)s * a.stride;
+	const unsigned off = a.offset ? a.offset[s] : 0u;
+	const unsigned n = a.nvalid[s];
+	const unsigned tmax = a.try_max[s];
+	unsigned tstep = a.try_step[s];
 	if (tstep == 0)
 	    tstep = 1;
-	const int sel = expect_sel ? (expect_sel[s] ? 1 : 0) : 0;
+	const int sel = a.expect_sel ? (a.expect_sel[s] ? 1 : 0) : 0;
 	unsigned long long bits = 0;
 	float ampl = 0.f, conf = 0.f;
 	unsigned start = 0;
 	if (tmax) {
-	    const unsigned need_end = off + tmax - 1u + geo.span;
 	    const unsigned from = off & ~3u;
-	    const unsigned to = (need_end + 3u) & ~3u;
-	    if (ring_floats && to - from <= ring_floats) {
+	    const unsigned to = (off + tmax - 1u + geo.span + 3u) & ~3u;
+	    if (MODE == 0 && to - from <= ring_floats) {
 		__syncwarp(gmask);
-		ring_fill<G>(sm.ring, mask, x, n, from, to, g);
+		ring_issue<G>(rg, x, n, off, off & 3u, from, to, g);
+		cp_async_commit();
+		cp_async_wait<0>();
 		__syncwarp(gmask);
-		RingSrc src = { sm.ring, mask };
-		conf = find_frame<G, RingSrc>(src, off, geo, sel, sm.tw, sm.scr, g, gmask,
-			try_first[s], tmax, tstep, limit[s], bits, ampl, start);
+		conf = find_frame_fast<G, W, L>(rg, off & 3u, geo, sel, sm.tw, sm.scr, g, gmask,
+			a.try_first[s], tmax, tstep, a.limit[s], bits, ampl, start);
 	    } else {
-		GlobalSrc src = { x, n };
+		const GlobalSrc src = { x, n };
 		conf = find_frame<G, GlobalSrc>(src, off, geo, sel, sm.tw, sm.scr, g, gmask,
-			try_first[s], tmax, tstep, limit[s], bits, ampl, start);
+			a.try_first[s], tmax, tstep, a.limit[s], bits, ampl, start);
 	    }
 	}
 	if (g == 0)
-	    store_frame(frames + s, bits, conf, ampl, start);
+	    store_frame(a.frames + s, bits, conf, ampl, start);
     }
 }
 
@@ -375,31 +157,26 @@ k_find_frame(const __grid_constant__ fsk_b200_geom geo, const float4 *__restrict
 /* K2: the rx loop (src/minimodem.c:1137-1463) for whole streams            */
 /* ------------------------------------------------------------------------ */
 
-template <int G, bool RING>
-__global__ void __launch_bounds__(256)
+template <int G, int W, int L, int MODE>
+__global__ void __launch_bounds__(128, 4)
 k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200_loopc lc,
 	const float4 *__restrict__ tw_global, unsigned tw_in_smem, unsigned ring_floats,
-	const float *__restrict__ samples, unsigned nstreams, size_t stride,
-	const uint32_t *__restrict__ nsamples, uint32_t nsamples_all,
-	fsk_b200_frame *__restrict__ frames, uint32_t max_frames,
-	fsk_b200_stream_state *__restrict__ states)
+	unsigned lookahead, const __grid_constant__ RxArgs a)
 {
     extern __shared__ float4 smem4[];
-    const unsigned wpb = blockDim.x >> 5;
-    const Smem sm = carve<G>(smem4, geo, tw_global, tw_in_smem, ring_floats, wpb);
-    const unsigned lane = threadIdx.x & 31, g = lane % G, sidx = lane / G, spw = 32 / G;
-    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (sidx * G));
-    const unsigned warp = threadIdx.x >> 5;
-    const unsigned mask = ring_floats ? ring_floats - 1u : 0u;
+    const Smem sm = carve<G>(smem4, geo, tw_global, tw_in_smem, ring_floats);
+    GROUP_VARS;
+    const Ring rg = { sm.ring, ring_floats, (geo.bit_nsamples + 3u) & ~3u };
+    const unsigned R = ring_floats;
 
-    for (unsigned s = (blockIdx.x * wpb + warp) * spw + sidx; s < nstreams;
+    for (unsigned s = (blockIdx.x * wpb + warp) * spw + sidx; s < a.nstreams;
 	    s += gridDim.x * wpb * spw) {
-	fsk_b200_stream_state st = states[s];
+	fsk_b200_stream_state st = a.states[s];
 	if (st.done)
 	    continue;
-	const float *x = samples + (size_t)s * stride;
-	const unsigned n = nsamples ? nsamples[s] : nsamples_all;
-	fsk_b200_frame *out = frames + (size_t)s * max_frames;
+	const float *x = a.samples + (size_t)s * a.stride;
+	const unsigned n = a.nsamples ? a.nsamples[s] : a.nsamples_all;
+	fsk_b200_frame *out = a.frames + (size_t)s * a.max_frames;
 
 	unsigned pos = (unsigned)st.pos;
 	unsigned nframes = st.nframes;
@@ -409,14 +186,25 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
 	float confidence_total = st.confidence_total, amplitude_total = st.amplitude_total;
 	unsigned nframes_decoded = st.nframes_decoded;
 	unsigned done = 0;
-	unsigned filled = pos & ~3u;		/* ring holds [filled_lo, filled) */
-	__syncwarp(gmask);
+
+	/* ring bookkeeping (MODE 0): ring offset of `pos`, and the absolute index up to
+	 * which copies have been ISSUED */
+	unsigned pos_off = pos & 3u;
+	unsigned filled = pos & ~3u;
+	const unsigned need_max = lc.try_max_nocarrier - 1u + geo.span;
+	if (MODE == 0) {
+	    __syncwarp(gmask);
+	    const unsigned to = min((pos + need_max + 3u) & ~3u, (pos & ~3u) + R);
+	    ring_issue<G>(rg, x, n, pos, pos_off, filled, to, g);
+	    cp_async_commit();
+	    filled = to;
+	}
 
 	for (;;) {
 	    if (pos >= n) { done = 1; break; }			/* :1176 */
 	    const unsigned remaining = n - pos;
 	    if (remaining < lc.expect_nsamples) { done = 1; break; }	/* :1229 */
-	    if (nframes >= max_frames)
+	    if (nframes >= a.max_frames)
 		break;						/* output full: resumable */
 
 	    unsigned try_max = carrier ? lc.try_max_carrier : lc.try_max_nocarrier;	/* :1236-1241 */
@@ -426,29 +214,30 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
 	    const unsigned try_first = carrier ? lc.nsamples_overscan : 0u;	/* :1263 */
 	    const int sel = carrier ? 0 : 1;			/* :1270 data / sync string */
 
+	    if (MODE == 0) {
+		/* prefetch what the NEXT iteration can need (it starts at most `lookahead`
+		 * samples further), then wait only for what THIS one needs */
+		const unsigned need_now = (pos + try_max - 1u + geo.span + 3u) & ~3u;
+		const unsigned to = min((pos + lookahead + need_max + 3u) & ~3u, (pos & ~3u) + R);
+		const bool late = filled < need_now;	/* part of this window is only now requested */
+		if (to > filled) {
+		    ring_issue<G>(rg, x, n, pos, pos_off, filled, to, g);
+		    filled = to;
+		}
+		cp_async_commit();
+		if (late)
+		    cp_async_wait<0>();
+		else
+		    cp_async_wait<1>();
+		__syncwarp(gmask);
+	    }
+	    const GlobalSrc gsrc = { x, n };
+
 	    unsigned long long bits;
 	    float amplitude, confidence;
 	    unsigned frame_start;
-	    unsigned long long bits2;
-	    float amplitude2, confidence2 = 0.f;
-	    unsigned frame_start2;
-	    bool want_refine;
-
-	    if (RING) {
-		const unsigned to = (pos + try_max - 1u + geo.span + 3u) & ~3u;
-		if (filled < (pos & ~3u))
-		    filled = pos & ~3u;		/* skipped ahead of everything fetched */
-		if (to > filled) {
-		    ring_fill<G>(sm.ring, mask, x, n, filled, to, g);
-		    filled = to;
-		}
-		__syncwarp(gmask);
-	    }
-	    const RingSrc rsrc = { sm.ring, mask };
-	    const GlobalSrc gsrc = { x, n };
-
-	    if (RING)
-		confidence = find_frame<G, RingSrc>(rsrc, pos, geo, sel, sm.tw, sm.scr, g, gmask,
+	    if (MODE == 0)
+		confidence = find_frame_fast<G, W, L>(rg, pos_off, geo, sel, sm.tw, sm.scr, g, gmask,
 			try_first, try_max, try_step, lc.confidence_search_limit,
 			bits, amplitude, frame_start);		/* :1265 */
 	    else
@@ -456,7 +245,7 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
 			try_first, try_max, try_step, lc.confidence_search_limit,
 			bits, amplitude, frame_start);
 
-	    want_refine = false;
+	    bool want_refine = false;
 	    if (confidence < peak_confidence * 0.75f) {		/* :1278-1282 */
 		want_refine = true;
 		peak_confidence = 0.f;
@@ -497,9 +286,12 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
 		    try_step = try_max / 8u;
 		    if (try_step == 0)
 			try_step = 1;
+		    unsigned long long bits2;
+		    float amplitude2, confidence2;
+		    unsigned frame_start2;
 		    /* `carrier` is 1 by now, so the data string is searched (:1378) */
-		    if (RING)
-			confidence2 = find_frame<G, RingSrc>(rsrc, pos, geo, 0, sm.tw, sm.scr, g,
+		    if (MODE == 0)
+			confidence2 = find_frame_fast<G, W, L>(rg, pos_off, geo, 0, sm.tw, sm.scr, g,
 				gmask, try_first, try_max, try_step, INFINITY,
 				bits2, amplitude2, frame_start2);
 		    else
@@ -526,9 +318,19 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
 	    }
 	    if (advance > remaining) { done = 1; break; }	/* :1151 */
 	    pos += advance;
-	    if (RING)
-		__syncwarp(gmask);	/* all reads of this window precede the next fill */
+	    if (MODE == 0) {
+		pos_off = ring_wrap(pos_off + advance, R);	/* advance < R by construction */
+		if (filled < (pos & ~3u)) {
+		    /* skipped past everything requested so far: restart the ring here */
+		    cp_async_wait<0>();
+		    filled = pos & ~3u;
+		    pos_off = pos & 3u;
+		}
+		__syncwarp(gmask);	/* every read of this window precedes the next copies */
+	    }
 	}
+	if (MODE == 0)
+	    cp_async_wait<0>();		/* nothing in flight into this ring slot when it is reused */
 
 	if (g == 0) {
 	    st.pos = pos;
@@ -542,7 +344,7 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
 	    st.amplitude_total = amplitude_total;
 	    st.nframes_decoded = nframes_decoded;
 	    st.done = done;
-	    states[s] = st;
+	    a.states[s] = st;
 	}
 	__syncwarp(gmask);
     }
@@ -728,16 +530,16 @@ extern "C" void fsk_b200_cuda_engine_destroy(void *p)
 extern "C" int fsk_b200_cuda_tune(void *p, int lanes, int wpb, int ring)
 {
     CudaEngine *ce = (CudaEngine *)p;
-    if (lanes && (lanes < 2 || lanes > 32 || (lanes & (lanes - 1)))) {
-	fsk_b200_set_error("lanes per stream must be a power of two in 2..32");
+    if (lanes && (lanes < 4 || lanes > 32 || (lanes & (lanes - 1)))) {
+	fsk_b200_set_error("lanes per stream must be 4, 8, 16 or 32");
 	return -EINVAL;
     }
-    if (ring && (ring < 64 || (ring & (ring - 1)))) {
-	fsk_b200_set_error("ring size must be a power of two >= 64");
+    if (ring && (ring < 64 || (ring & 3))) {
+	fsk_b200_set_error("ring size must be a multiple of 4 floats, >= 64");
 	return -EINVAL;
     }
-    if (wpb < 0 || wpb > 8) {
-	fsk_b200_set_error("warps per block must be 1..8");
+    if (wpb < 0 || wpb > 4) {
+	fsk_b200_set_error("warps per block must be 1..4");
 	return -EINVAL;
     }
     ce->lanes = lanes;
@@ -798,46 +600,80 @@ extern "C" int fsk_b200_cuda_set_table(void *p, int fftsize, unsigned b_mark, un
 
 /* launch shape shared by K1 and K2 */
 struct Shape {
-    int G, wpb, blocks;
-    unsigned ring, tw_in_smem;
+    int G, W, L, mode, wpb, blocks;
+    unsigned ring, tw_in_smem, lookahead;
     size_t smem;
     fsk_b200_geom geo;
 };
 
-static unsigned pow2_ceil(unsigned v)
+/* (G, W, L) combinations that are instantiated for the fast path */
+static bool fast_combo(int G, int W, int L)
 {
-    unsigned p = 1;
-    while (p < v)
-	p <<= 1;
-    return p;
+    if (L > 1)
+	return W == 1 && ((G == 16 && L == 2) || (G == 32 && (L == 2 || L == 4)) || (G == 8 && L == 2));
+    switch (G) {
+	case 4: return W >= 2 && W <= 4;
+	case 8: return W >= 1 && W <= 4;
+	case 16: return W >= 1 && W <= 4;
+	case 32: return W >= 1 && W <= 2;
+    }
+    return false;
+}
+
+static void split_for(int G, unsigned n_bits, int *W, int *L)
+{
+    /* windows per lane, or lanes per window when there are more lanes than windows */
+    int l = 1;
+    while ((unsigned)(l * 2) * n_bits <= (unsigned)G)
+	l *= 2;
+    *L = l;
+    const unsigned wpp = (unsigned)G / (unsigned)l;
+    *W = (int)((n_bits + wpp - 1) / wpp);
 }
 
 static int pick_shape(const CudaEngine *ce, const fsk_b200_geom *g, unsigned need_floats,
-	size_t nstreams, Shape *sh)
+	unsigned max_advance, size_t nstreams, Shape *sh)
 {
     sh->geo = *g;
     const size_t smem_max = (size_t)ce->smem_optin;
-    /* twiddle table in shared memory when it is small next to the rings */
     const size_t tw_bytes = (size_t)g->bit_nsamples * sizeof(float4);
     sh->tw_in_smem = tw_bytes <= 24 * 1024;
     const size_t fixed = sh->tw_in_smem ? tw_bytes : 0;
+    const size_t pad_bytes = (size_t)((g->bit_nsamples + 3u) & ~3u) * 4;
+    const size_t scr_bytes = (size_t)g->n_bits * sizeof(float2) + pad_bytes;	/* per stream, besides the ring */
 
-    unsigned ring = ce->ring ? (unsigned)ce->ring : pow2_ceil(need_floats + 8u);
-    if (ring < 64)
-	ring = 64;
+    /* ring: the widest search window plus (ideally) one full advance of look-ahead */
+    const unsigned ring_min = (need_floats + 8u + 3u) & ~3u;
+    unsigned ring = ce->ring ? (((unsigned)ce->ring + 3u) & ~3u) : ((need_floats + max_advance + 8u + 3u) & ~3u);
+    if (ring < ring_min)
+	ring = ring_min;
+    /* keep at least ~24 streams per SM resident if that is possible at all */
+    if (!ce->ring) {
+	while (ring > ring_min && (smem_max - fixed) / ((size_t)ring * 4 + scr_bytes) < 24)
+	    ring = (ring_min + ring) / 2 & ~3u;
+	if (ring < ring_min)
+	    ring = ring_min;
+    }
+
     int G = ce->lanes;
     if (!G) {
-	/* aim for >= 512 resident threads per SM given how many rings fit */
-	const size_t per_stream = (size_t)ring * 4 + (size_t)g->n_bits * 8;
+	const size_t per_stream = (size_t)ring * 4 + scr_bytes;
 	size_t streams_per_sm = (smem_max > fixed ? smem_max - fixed : 0) / (per_stream ? per_stream : 1);
 	if (streams_per_sm < 1)
 	    streams_per_sm = 1;
-	G = 4;
+	G = 8;
 	while (G < 32 && streams_per_sm * (size_t)G < 512)
 	    G <<= 1;
     }
+    int W, L;
+    split_for(G, g->n_bits, &W, &L);
+    while (!fast_combo(G, W, L) && G < 32) {	/* e.g. 47-bit frames need G >= 16 */
+	G <<= 1;
+	split_for(G, g->n_bits, &W, &L);
+    }
+    bool fast = fast_combo(G, W, L) && g->bit_nsamples <= FAST_MAX_N * (unsigned)L;
+
     int wpb = ce->wpb ? ce->wpb : 2;
-    const size_t scr_bytes = (size_t)g->n_bits * sizeof(float2);
     for (;;) {
 	const size_t spw = 32 / G;
 	const size_t smem = (fixed + (size_t)wpb * spw * ((size_t)ring * 4 + scr_bytes) + 15) & ~(size_t)15;
@@ -846,19 +682,39 @@ static int pick_shape(const CudaEngine *ce, const fsk_b200_geom *g, unsigned nee
 	    break;
 	}
 	if (wpb > 1) { wpb--; continue; }
-	if (G < 32) { G <<= 1; continue; }
-	if (ring) { ring = 0; continue; }	/* not even one ring fits: read global memory directly */
+	if (G < 32) {
+	    G <<= 1;
+	    split_for(G, g->n_bits, &W, &L);
+	    fast = fast_combo(G, W, L) && g->bit_nsamples <= FAST_MAX_N * (unsigned)L;
+	    continue;
+	}
+	if (ring) { ring = 0; fast = false; continue; }	/* not even one ring fits: read global memory */
 	sh->tw_in_smem = 0;
-	sh->smem = (scr_bytes + 15) & ~(size_t)15;
+	sh->smem = ((size_t)g->n_bits * sizeof(float2) + 15) & ~(size_t)15;
 	break;
     }
+    if (!fast) {
+	/* generic kernels are instantiated for G = 32 only and do not use a ring */
+	G = 32;
+	ring = 0;
+	split_for(G, g->n_bits, &W, &L);
+	const size_t fixed2 = sh->tw_in_smem ? tw_bytes : 0;
+	const size_t scr_only = (size_t)g->n_bits * sizeof(float2);
+	wpb = ce->wpb ? ce->wpb : 4;
+	sh->smem = (fixed2 + (size_t)wpb * scr_only + 15) & ~(size_t)15;
+	if (sh->smem > smem_max) {
+	    sh->tw_in_smem = 0;
+	    sh->smem = ((size_t)wpb * scr_only + 15) & ~(size_t)15;
+	}
+    }
+    sh->mode = fast ? 0 : 1;
     sh->G = G;
+    sh->W = W;
+    sh->L = L;
     sh->wpb = wpb;
     sh->ring = ring;
-    unsigned L = 1;
-    while (L * 2 * g->n_bits <= (unsigned)G)
-	L *= 2;
-    sh->geo.lanes_per_window = L;
+    sh->lookahead = ring > ring_min ? (ring - ring_min < max_advance ? ring - ring_min : max_advance) : 0;
+    sh->geo.lanes_per_window = (unsigned)L;
     /* one block per wpb*(32/G) streams: the hardware block scheduler hands out
      * streams as SM resources free up (streams differ in length and work) */
     const size_t streams_per_block = (size_t)wpb * (32 / G);
@@ -869,19 +725,22 @@ static int pick_shape(const CudaEngine *ce, const fsk_b200_geom *g, unsigned nee
     return 0;
 }
 
-template <int G>
-static cudaError_t launch_find(const Shape &sh, const CudaEngine *ce, const float *samples,
-	size_t nstreams, size_t stride, const uint32_t *offset, const uint32_t *nvalid,
-	const uint32_t *try_first, const uint32_t *try_max, const uint32_t *try_step,
-	const float *limit, const uint8_t *expect_sel, fsk_b200_frame *frames, cudaStream_t st)
+/* compile-time dispatch over the instantiated (G, W, L) combinations */
+#define FAST_COMBOS(X) \
+    X(4, 2, 1) X(4, 3, 1) X(4, 4, 1) \
+    X(8, 1, 1) X(8, 2, 1) X(8, 3, 1) X(8, 4, 1) X(8, 1, 2) \
+    X(16, 1, 1) X(16, 2, 1) X(16, 3, 1) X(16, 4, 1) X(16, 1, 2) \
+    X(32, 1, 1) X(32, 2, 1) X(32, 1, 2) X(32, 1, 4)
+
+template <int G, int W, int L, int MODE>
+static cudaError_t launch_find_t(const Shape &sh, const CudaEngine *ce, const FindArgs &a, cudaStream_t st)
 {
-    cudaError_t e = cudaFuncSetAttribute(k_find_frame<G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-	    (int)sh.smem);
+    cudaError_t e = cudaFuncSetAttribute(k_find_frame<G, W, L, MODE>,
+	    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh.smem);
     if (e != cudaSuccess)
 	return e;
-    k_find_frame<G><<<sh.blocks, sh.wpb * 32, sh.smem, st>>>(sh.geo, ce->d_tw, sh.tw_in_smem, sh.ring,
-	    samples, (unsigned)nstreams, stride, offset, nvalid, try_first, try_max, try_step, limit,
-	    expect_sel, frames);
+    k_find_frame<G, W, L, MODE><<<sh.blocks, sh.wpb * 32, sh.smem, st>>>(sh.geo, ce->d_tw,
+	    sh.tw_in_smem, sh.ring, a);
     g_launches++;
     return cudaGetLastError();
 }
@@ -898,49 +757,36 @@ extern "C" int fsk_b200_cuda_find_frame_batch(void *p, const fsk_b200_geom *g, c
     }
     Shape sh;
     /* the ring is sized for the widest search of the rx loop: 1.5 bits + span */
-    const unsigned need = g->span + 2u * g->bit_nsamples + 8u;
-    pick_shape(ce, g, need, nstreams, &sh);
+    pick_shape(ce, g, g->span + 2u * g->bit_nsamples + 8u, 0, nstreams, &sh);
+    const FindArgs a = { samples, (unsigned)nstreams, stride, offset, nvalid, try_first, try_max,
+	try_step, limit, expect_sel, frames };
     cudaStream_t st = (cudaStream_t)stream;
-    cudaError_t e;
-#define FF(GG) e = launch_find<GG>(sh, ce, samples, nstreams, stride, offset, nvalid, try_first, \
-	try_max, try_step, limit, expect_sel, frames, st)
-    switch (sh.G) {
-	case 2: FF(2); break;
-	case 4: FF(4); break;
-	case 8: FF(8); break;
-	case 16: FF(16); break;
-	default: FF(32); break;
+    cudaError_t e = cudaErrorInvalidValue;
+    if (sh.mode == 0) {
+#define X(GG, WW, LL) if (sh.G == GG && sh.W == WW && sh.L == LL) e = launch_find_t<GG, WW, LL, 0>(sh, ce, a, st);
+	FAST_COMBOS(X)
+#undef X
+    } else {
+	e = launch_find_t<32, 1, 1, 1>(sh, ce, a, st);
     }
-#undef FF
     if (e != cudaSuccess) {
-	fsk_b200_set_error("find_frame_batch launch: %s", cudaGetErrorString(e));
+	fsk_b200_set_error("find_frame_batch launch (G=%d W=%d L=%d mode=%d smem=%zu): %s", sh.G, sh.W,
+		sh.L, sh.mode, sh.smem, cudaGetErrorString(e));
 	return -EIO;
     }
     return 0;
 }
 
-template <int G>
-static cudaError_t launch_rx(const Shape &sh, const CudaEngine *ce, const fsk_b200_loopc *lc,
-	const float *samples, size_t nstreams, size_t stride, const uint32_t *nsamples,
-	uint32_t nsamples_all, fsk_b200_frame *frames, uint32_t max_frames,
-	fsk_b200_stream_state *states, cudaStream_t st)
+template <int G, int W, int L, int MODE>
+static cudaError_t launch_rx_t(const Shape &sh, const CudaEngine *ce, const fsk_b200_loopc *lc,
+	const RxArgs &a, cudaStream_t st)
 {
-    cudaError_t e;
-    if (sh.ring) {
-	e = cudaFuncSetAttribute(k_rx<G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh.smem);
-	if (e != cudaSuccess)
-	    return e;
-	k_rx<G, true><<<sh.blocks, sh.wpb * 32, sh.smem, st>>>(sh.geo, *lc, ce->d_tw, sh.tw_in_smem,
-		sh.ring, samples, (unsigned)nstreams, stride, nsamples, nsamples_all, frames,
-		max_frames, states);
-    } else {
-	e = cudaFuncSetAttribute(k_rx<G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh.smem);
-	if (e != cudaSuccess)
-	    return e;
-	k_rx<G, false><<<sh.blocks, sh.wpb * 32, sh.smem, st>>>(sh.geo, *lc, ce->d_tw, sh.tw_in_smem,
-		0u, samples, (unsigned)nstreams, stride, nsamples, nsamples_all, frames,
-		max_frames, states);
-    }
+    cudaError_t e = cudaFuncSetAttribute(k_rx<G, W, L, MODE>,
+	    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh.smem);
+    if (e != cudaSuccess)
+	return e;
+    k_rx<G, W, L, MODE><<<sh.blocks, sh.wpb * 32, sh.smem, st>>>(sh.geo, *lc, ce->d_tw, sh.tw_in_smem,
+	    sh.ring, sh.lookahead, a);
     g_launches++;
     return cudaGetLastError();
 }
@@ -958,21 +804,22 @@ extern "C" int fsk_b200_cuda_rx_batch(void *p, const fsk_b200_geom *g, const fsk
     Shape sh;
     const unsigned tmax = lc->try_max_nocarrier > lc->try_max_carrier
 	? lc->try_max_nocarrier : lc->try_max_carrier;
-    pick_shape(ce, g, tmax + g->span + 8u, nstreams, &sh);
+    const unsigned max_advance = tmax - 1u + lc->frame_nsamples;	/* :1407, overscan >= 0 */
+    pick_shape(ce, g, tmax - 1u + g->span, max_advance, nstreams, &sh);
+    const RxArgs a = { samples, (unsigned)nstreams, stride, nsamples, nsamples_all, frames, max_frames,
+	states };
     cudaStream_t st = (cudaStream_t)stream;
-    cudaError_t e;
-#define RX(GG) e = launch_rx<GG>(sh, ce, lc, samples, nstreams, stride, nsamples, nsamples_all, \
-	frames, max_frames, states, st)
-    switch (sh.G) {
-	case 2: RX(2); break;
-	case 4: RX(4); break;
-	case 8: RX(8); break;
-	case 16: RX(16); break;
-	default: RX(32); break;
+    cudaError_t e = cudaErrorInvalidValue;
+    if (sh.mode == 0) {
+#define X(GG, WW, LL) if (sh.G == GG && sh.W == WW && sh.L == LL) e = launch_rx_t<GG, WW, LL, 0>(sh, ce, lc, a, st);
+	FAST_COMBOS(X)
+#undef X
+    } else {
+	e = launch_rx_t<32, 1, 1, 1>(sh, ce, lc, a, st);
     }
-#undef RX
     if (e != cudaSuccess) {
-	fsk_b200_set_error("rx_batch launch: %s", cudaGetErrorString(e));
+	fsk_b200_set_error("rx_batch launch (G=%d W=%d L=%d mode=%d ring=%u smem=%zu): %s", sh.G, sh.W,
+		sh.L, sh.mode, sh.ring, sh.smem, cudaGetErrorString(e));
 	return -EIO;
     }
     return 0;
