@@ -4,12 +4,13 @@
  * Two implementations of the same arithmetic:
  *
  *  FAST   frame_analyze_fast<G,W,L> / find_frame_fast: the stream's samples are in a
- *         per-stream shared-memory ring of R floats (R % 4 == 0); a window is read
- *         through plain pointers (the one window of a frame that straddles the
- *         ring end is split in two runs); each lane owns W windows and walks the
- *         twiddle table once for all of them (n outer, windows inner): one
- *         LDS.128 (twiddles) + W LDS.32 (samples) feed 4*W FMAs.  W, L are
- *         compile-time so accumulators stay in registers.
+ *         per-stream shared-memory ring of R floats (R % 4 == 0) whose first
+ *         window-length is mirrored behind its end, so a bit window is always one
+ *         linear run; each lane owns W windows (and 1/L of their samples) and
+ *         walks the twiddle table once for all of them (n outer, windows inner):
+ *         one LDS.128 (twiddles) + W LDS.32 (samples) feed 4*W FMAs.  W, L are
+ *         compile-time so accumulators and per-bit results stay in registers;
+ *         frame statistics are butterfly-reduced over the group.
  *  GENERIC frame_analyze<G,Src> / find_frame: any source (ring with mask, or
  *         global memory), run-time window split, fp64 folding for very long
  *         windows.  Used when the windows do not fit shared memory (e.g. 0.5
@@ -267,9 +268,41 @@ struct Ring {
 
 __device__ __forceinline__ unsigned ring_wrap(unsigned off, unsigned R) { return off >= R ? off - R : off; }
 
+/* butterfly all-reduce over the G lanes of a group (every lane ends with the total) */
+template <int G>
+__device__ __forceinline__ float group_sum(float v, unsigned gmask)
+{
+#pragma unroll
+    for (int o = G >> 1; o; o >>= 1)
+	v += __shfl_xor_sync(gmask, v, o);
+    return v;
+}
+template <int G>
+__device__ __forceinline__ unsigned group_or(unsigned v, unsigned gmask)
+{
+#pragma unroll
+    for (int o = G >> 1; o; o >>= 1)
+	v |= __shfl_xor_sync(gmask, v, o);
+    return v;
+}
+template <int G>
+__device__ __forceinline__ unsigned group_add(unsigned v, unsigned gmask)
+{
+#pragma unroll
+    for (int o = G >> 1; o; o >>= 1)
+	v += __shfl_xor_sync(gmask, v, o);
+    return v;
+}
+
+/* One candidate frame start, fast path.  Lane g of the group owns the windows
+ * w = j*(G/L) + g/L (j < W) and, of each, the samples n = g%L, g%L + L, ...
+ * Everything stays in registers: the per-bit (sig, noise, bit) values never go
+ * to memory, and the frame statistics of src/fsk.c:271-336 are formed by
+ * butterfly reductions over the group instead of a serial loop over the bits
+ * (same terms, different but fixed summation order). */
 template <int G, int W, int L>
 __device__ __forceinline__ float frame_analyze_fast(const Ring rg, unsigned cand_off,
-	const fsk_b200_geom &geo, int sel, const float4 *__restrict__ tw, float2 *scr,
+	const fsk_b200_geom &geo, int sel, const float4 *__restrict__ tw,
 	unsigned g, unsigned gmask, unsigned long long &bits_out, float &ampl_out)
 {
     /* cand_off: ring offset (< R) of the candidate's first sample */
@@ -277,7 +310,7 @@ __device__ __forceinline__ float frame_analyze_fast(const Ring rg, unsigned cand
     const unsigned N = geo.bit_nsamples, nb = geo.n_bits, R = rg.R;
     const unsigned part = g % L, wslot = g / L;
 
-    /* this lane's windows: w = j*WPP + wslot (slots past n_bits read window 0: harmless) */
+    /* slots past n_bits read window 0: harmless, their results are dropped */
     const float *p[W];
 #pragma unroll
     for (int j = 0; j < W; j++) {
@@ -290,7 +323,6 @@ __device__ __forceinline__ float frame_analyze_fast(const Ring rg, unsigned cand
     for (int j = 0; j < W; j++)
 	acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
 
-    __syncwarp(gmask);				/* previous readers of scr are done */
 #pragma unroll 4
     for (unsigned n = part; n < N; n += L) {
 	const float4 c = tw[n];
@@ -303,21 +335,31 @@ __device__ __forceinline__ float frame_analyze_fast(const Ring rg, unsigned cand
 	    acc[j][3] = fmaf(x, c.w, acc[j][3]);
 	}
     }
-
     if (L > 1) {
 #pragma unroll
 	for (int o = L >> 1; o; o >>= 1) {
 #pragma unroll
-	    for (int k = 0; k < 4; k++)
-		acc[0][k] += __shfl_xor_sync(gmask, acc[0][k], o);
+	    for (int j = 0; j < W; j++) {
+#pragma unroll
+		for (int k = 0; k < 4; k++)
+		    acc[j][k] += __shfl_xor_sync(gmask, acc[j][k], o);
+	    }
 	}
     }
 
+    /* per-window decision (src/fsk.c:158-169) and this lane's share of the sums (:271-289) */
+    float ts = 0.f, tn = 0.f, am = 0.f, as = 0.f;
+    unsigned nm = 0, blo = 0, bhi = 0;
+    float sig[W];
+    bool one[W], own[W];
     bool mismatch = false;
 #pragma unroll
     for (int j = 0; j < W; j++) {
 	const unsigned w = j * WPP + wslot;
-	if (w < nb && part == 0) {
+	own[j] = w < nb && part == 0;
+	sig[j] = 0.f;
+	one[j] = false;
+	if (own[j]) {
 	    float mag_mark = sqrtf(acc[j][0] * acc[j][0] + acc[j][1] * acc[j][1]) * geo.mag_scalar;
 	    float mag_space = sqrtf(acc[j][2] * acc[j][2] + acc[j][3] * acc[j][3]) * geo.mag_scalar;
 	    if (needs_resum(mag_mark, mag_space)) {
@@ -335,35 +377,69 @@ __device__ __forceinline__ float frame_analyze_fast(const Ring rg, unsigned cand
 		mag_mark = sqrtf(frm * frm + fim * fim) * geo.mag_scalar;
 		mag_space = sqrtf(frs * frs + fis * fis) * geo.mag_scalar;
 	    }
-	    mismatch |= decide_bit(mag_mark, mag_space, geo.expect[sel][w], scr + w);
+	    one[j] = mag_mark > mag_space;			/* strict: tie -> space */
+	    sig[j] = one[j] ? mag_mark : mag_space;
+	    const float noise = one[j] ? mag_space : mag_mark;
+	    const unsigned e = geo.expect[sel][w];
+	    mismatch |= e != 2u && e != (one[j] ? 1u : 0u);	/* pass 1, :211 */
+	    ts += sig[j];
+	    if (noise > FSK_FLT_EPSILON)			/* :279 */
+		tn += noise;
+	    if (one[j]) {
+		am += sig[j];
+		nm++;
+		if (w < 32u) blo |= 1u << w; else bhi |= 1u << (w - 32u);
+	    } else {
+		as += sig[j];
+	    }
 	}
     }
-    __syncwarp(gmask);
     if (__any_sync(gmask, mismatch)) {		/* pass 1 reject, src/fsk.c:211-212 */
 	bits_out = 0;
 	ampl_out = 0.f;
 	return 0.f;
     }
-    return confidence_from_scratch(scr, nb, gmask, [&](auto body) {
-	if (part == 0) {
+    ts = group_sum<G>(ts, gmask);
+    tn = group_sum<G>(tn, gmask);
+    am = group_sum<G>(am, gmask);
+    as = group_sum<G>(as, gmask);
+    nm = group_add<G>(nm, gmask);
+    blo = group_or<G>(blo, gmask);
+    if (nb > 32u)
+	bhi = group_or<G>(bhi, gmask);
+
+    const unsigned n_space = nb - nm;
+    const float snr = ts / tn;					/* :292, may be +inf */
+    const float avg_bit_sig = ts / (float)(int)nb;		/* :295 */
+    if (nm)
+	am = am / (float)nm;					/* :298-301 */
+    if (n_space)
+	as = as / (float)n_space;
+    float dv = 0.f;						/* :305-311 */
 #pragma unroll
-	    for (int j = 0; j < W; j++) {
-		const unsigned w = j * WPP + wslot;
-		if (w < nb)
-		    body(w);
-	    }
+    for (int j = 0; j < W; j++) {
+	if (own[j]) {
+	    const float other = one[j] ? am : as;
+	    dv += fabsf(sig[j] - other) / other;
 	}
-    }, bits_out, ampl_out);
+    }
+    float divergence = group_sum<G>(dv, gmask);
+    divergence *= 2.f;						/* :312-313 */
+    divergence = divergence / (float)(int)nb;
+
+    bits_out = ((unsigned long long)bhi << 32) | blo;
+    ampl_out = avg_bit_sig;					/* :342 */
+    return snr * (1.0f - divergence);				/* :336 */
 }
 
 template <int G, int W, int L>
 __device__ __forceinline__ float find_frame_fast(const Ring rg, unsigned pos_off,
-	const fsk_b200_geom &geo, int sel, const float4 *__restrict__ tw, float2 *scr,
+	const fsk_b200_geom &geo, int sel, const float4 *__restrict__ tw,
 	unsigned g, unsigned gmask, unsigned try_first, unsigned try_max, unsigned try_step,
 	float limit, unsigned long long &best_bits, float &best_a, unsigned &best_t)
 {
     return search_frames([&](unsigned t, unsigned long long &bits, float &a) {
-	return frame_analyze_fast<G, W, L>(rg, ring_wrap(pos_off + t, rg.R), geo, sel, tw, scr,
+	return frame_analyze_fast<G, W, L>(rg, ring_wrap(pos_off + t, rg.R), geo, sel, tw,
 		g, gmask, bits, a);
     }, try_first, try_max, try_step, limit, best_bits, best_a, best_t);
 }

@@ -140,7 +140,7 @@ k_find_frame(const __grid_constant__ fsk_b200_geom geo, const float4 *__restrict
 		cp_async_commit();
 		cp_async_wait<0>();
 		__syncwarp(gmask);
-		conf = find_frame_fast<G, W, L>(rg, off & 3u, geo, sel, sm.tw, sm.scr, g, gmask,
+		conf = find_frame_fast<G, W, L>(rg, off & 3u, geo, sel, sm.tw, g, gmask,
 			a.try_first[s], tmax, tstep, a.limit[s], bits, ampl, start);
 	    } else {
 		const GlobalSrc src = { x, n };
@@ -237,7 +237,7 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
 	    float amplitude, confidence;
 	    unsigned frame_start;
 	    if (MODE == 0)
-		confidence = find_frame_fast<G, W, L>(rg, pos_off, geo, sel, sm.tw, sm.scr, g, gmask,
+		confidence = find_frame_fast<G, W, L>(rg, pos_off, geo, sel, sm.tw, g, gmask,
 			try_first, try_max, try_step, lc.confidence_search_limit,
 			bits, amplitude, frame_start);		/* :1265 */
 	    else
@@ -291,7 +291,7 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
 		    unsigned frame_start2;
 		    /* `carrier` is 1 by now, so the data string is searched (:1378) */
 		    if (MODE == 0)
-			confidence2 = find_frame_fast<G, W, L>(rg, pos_off, geo, 0, sm.tw, sm.scr, g,
+			confidence2 = find_frame_fast<G, W, L>(rg, pos_off, geo, 0, sm.tw, g,
 				gmask, try_first, try_max, try_step, INFINITY,
 				bits2, amplitude2, frame_start2);
 		    else
@@ -460,7 +460,7 @@ struct CudaEngine {
     int tw_fftsize;
     unsigned tw_bm, tw_bs;
     /* tuning (0 = automatic) */
-    int lanes, wpb, ring;
+    int lanes, wpb, ring, split;
     /* single-stream staging */
     float *d_one;
     size_t d_one_cap;
@@ -504,6 +504,7 @@ extern "C" void *fsk_b200_cuda_engine_new(void)
     if ((e = getenv("FSK_B200_LANES"))) ce->lanes = atoi(e);
     if ((e = getenv("FSK_B200_WPB"))) ce->wpb = atoi(e);
     if ((e = getenv("FSK_B200_RING"))) ce->ring = atoi(e);
+    if ((e = getenv("FSK_B200_SPLIT"))) ce->split = atoi(e);
     return ce;
 }
 
@@ -606,29 +607,44 @@ struct Shape {
     fsk_b200_geom geo;
 };
 
-/* (G, W, L) combinations that are instantiated for the fast path */
+/* (G, W, L) combinations that are instantiated for the fast path: G lanes per
+ * stream, L lanes per bit window, W windows per lane (W * G/L >= n_bits) */
+#define FAST_COMBOS(X) \
+    X(4, 1, 1) X(4, 2, 1) X(4, 3, 1) X(4, 4, 1) X(4, 2, 2) X(4, 4, 2) \
+    X(8, 1, 1) X(8, 2, 1) X(8, 3, 1) X(8, 4, 1) X(8, 1, 2) X(8, 2, 2) X(8, 3, 2) X(8, 4, 2) X(8, 4, 4) \
+    X(16, 1, 1) X(16, 2, 1) X(16, 3, 1) X(16, 4, 1) X(16, 1, 2) X(16, 2, 2) X(16, 3, 2) X(16, 4, 2) \
+    X(16, 1, 4) X(16, 2, 4) X(16, 3, 4) X(16, 4, 4) \
+    X(32, 1, 1) X(32, 2, 1) X(32, 1, 2) X(32, 2, 2) X(32, 3, 2) X(32, 4, 2) X(32, 1, 4) X(32, 2, 4) X(32, 3, 4) X(32, 4, 4)
+
 static bool fast_combo(int G, int W, int L)
 {
-    if (L > 1)
-	return W == 1 && ((G == 16 && L == 2) || (G == 32 && (L == 2 || L == 4)) || (G == 8 && L == 2));
-    switch (G) {
-	case 4: return W >= 2 && W <= 4;
-	case 8: return W >= 1 && W <= 4;
-	case 16: return W >= 1 && W <= 4;
-	case 32: return W >= 1 && W <= 2;
-    }
+#define X(GG, WW, LL) if (G == GG && W == WW && L == LL) return true;
+    FAST_COMBOS(X)
+#undef X
     return false;
 }
 
-static void split_for(int G, unsigned n_bits, int *W, int *L)
+/* best (W, L) for a group of G lanes: highest lane utilisation n_bits / (W * G/L);
+ * ties go to the larger L (neighbouring lanes then read neighbouring samples, which
+ * spreads the shared-memory banks) */
+static bool split_for(int G, unsigned n_bits, int force_L, int *W, int *L)
 {
-    /* windows per lane, or lanes per window when there are more lanes than windows */
-    int l = 1;
-    while ((unsigned)(l * 2) * n_bits <= (unsigned)G)
-	l *= 2;
-    *L = l;
-    const unsigned wpp = (unsigned)G / (unsigned)l;
-    *W = (int)((n_bits + wpp - 1) / wpp);
+    double best = -1.0;
+    for (int l = 1; l <= 4 && l <= G; l *= 2) {
+	if (force_L && l != force_L)
+	    continue;
+	const unsigned wpp = (unsigned)(G / l);
+	const unsigned w = (n_bits + wpp - 1) / wpp;
+	if (w > 4 || !fast_combo(G, (int)w, l))
+	    continue;
+	const double util = (double)n_bits / (double)(w * wpp);
+	if (util >= best - 1e-9) {
+	    best = util;
+	    *W = (int)w;
+	    *L = l;
+	}
+    }
+    return best > 0.0;
 }
 
 static int pick_shape(const CudaEngine *ce, const fsk_b200_geom *g, unsigned need_floats,
@@ -665,13 +681,14 @@ static int pick_shape(const CudaEngine *ce, const fsk_b200_geom *g, unsigned nee
 	while (G < 32 && streams_per_sm * (size_t)G < 512)
 	    G <<= 1;
     }
-    int W, L;
-    split_for(G, g->n_bits, &W, &L);
-    while (!fast_combo(G, W, L) && G < 32) {	/* e.g. 47-bit frames need G >= 16 */
+    int W = 1, L = 1;
+    bool fast = split_for(G, g->n_bits, ce->split, &W, &L);
+    while (!fast && G < 32) {			/* e.g. 47-bit frames need G >= 16 */
 	G <<= 1;
-	split_for(G, g->n_bits, &W, &L);
+	fast = split_for(G, g->n_bits, ce->split, &W, &L);
     }
-    bool fast = fast_combo(G, W, L) && g->bit_nsamples <= FAST_MAX_N * (unsigned)L;
+    if (g->bit_nsamples > FAST_MAX_N * (unsigned)L)
+	fast = false;
 
     int wpb = ce->wpb ? ce->wpb : 2;
     for (;;) {
@@ -684,8 +701,7 @@ static int pick_shape(const CudaEngine *ce, const fsk_b200_geom *g, unsigned nee
 	if (wpb > 1) { wpb--; continue; }
 	if (G < 32) {
 	    G <<= 1;
-	    split_for(G, g->n_bits, &W, &L);
-	    fast = fast_combo(G, W, L) && g->bit_nsamples <= FAST_MAX_N * (unsigned)L;
+	    fast = split_for(G, g->n_bits, ce->split, &W, &L) && g->bit_nsamples <= FAST_MAX_N * (unsigned)L;
 	    continue;
 	}
 	if (ring) { ring = 0; fast = false; continue; }	/* not even one ring fits: read global memory */
@@ -697,7 +713,10 @@ static int pick_shape(const CudaEngine *ce, const fsk_b200_geom *g, unsigned nee
 	/* generic kernels are instantiated for G = 32 only and do not use a ring */
 	G = 32;
 	ring = 0;
-	split_for(G, g->n_bits, &W, &L);
+	L = 1;
+	while ((unsigned)(L * 2) * g->n_bits <= 32u)
+	    L *= 2;
+	W = (int)((g->n_bits + 32 / L - 1) / (32 / L));
 	const size_t fixed2 = sh->tw_in_smem ? tw_bytes : 0;
 	const size_t scr_only = (size_t)g->n_bits * sizeof(float2);
 	wpb = ce->wpb ? ce->wpb : 4;
@@ -724,13 +743,6 @@ static int pick_shape(const CudaEngine *ce, const fsk_b200_geom *g, unsigned nee
     sh->blocks = (int)(blocks ? blocks : 1);
     return 0;
 }
-
-/* compile-time dispatch over the instantiated (G, W, L) combinations */
-#define FAST_COMBOS(X) \
-    X(4, 2, 1) X(4, 3, 1) X(4, 4, 1) \
-    X(8, 1, 1) X(8, 2, 1) X(8, 3, 1) X(8, 4, 1) X(8, 1, 2) \
-    X(16, 1, 1) X(16, 2, 1) X(16, 3, 1) X(16, 4, 1) X(16, 1, 2) \
-    X(32, 1, 1) X(32, 2, 1) X(32, 1, 2) X(32, 1, 4)
 
 template <int G, int W, int L, int MODE>
 static cudaError_t launch_find_t(const Shape &sh, const CudaEngine *ce, const FindArgs &a, cudaStream_t st)

@@ -319,8 +319,10 @@ def test_roundtrip_property_large_batch(mode, kw, nstreams, nwords):
     p = eng.params
     gen = torch.Generator(device="cpu").manual_seed(11)
     words = torch.randint(0, 1 << m.n_data_bits, (nstreams, nwords), generator=gen, dtype=torch.int32)
-    if m.do_rx_sync:            # the sync byte itself is suppressed by the rx (:1436-1439)
-        words[words == (m.sync_byte & 0xFF)] = 0x55
+    if m.do_rx_sync:
+        # no start/stop bits: the reference itself slips a bit on bytes without transitions
+        # (0xFF, checked with the oracle), so use the printable payload real SAME headers carry
+        words = torch.randint(32, 127, (nstreams, nwords), generator=gen, dtype=torch.int32)
     lead = torch.randint(0, int(d.nsamples_per_bit), (nstreams,), generator=gen, dtype=torch.int32)
     if m.do_rx_sync:
         # without start/stop bits the reference can lock one bit off when silence precedes the
