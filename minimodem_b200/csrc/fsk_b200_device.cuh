@@ -453,36 +453,161 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int NKEEP>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" :: "n"(NKEEP) : "memory"); }
 
+__device__ __forceinline__ void ldgsts16(unsigned dst, const float *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" :: "r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void ldgsts16_zfill(unsigned dst, const float *src, unsigned valid)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" :: "r"(dst), "l"(src), "r"(valid) : "memory");
+}
+
+/* one linear run of `count` floats (multiple of 4): lanes take 16-byte chunks round-robin */
+template <int G>
+__device__ __forceinline__ void ring_run(unsigned dst, const float *__restrict__ src, unsigned count,
+	unsigned g)
+{
+    dst += 16u * g;
+    src += 4u * g;
+#pragma unroll 4
+    for (unsigned c = 4u * g; c < count; c += 4u * G, dst += 16u * G, src += 4 * G)
+	ldgsts16(dst, src);
+}
+
 /* copies absolute indices [from, to) (multiples of 4) of stream x (valid length n)
  * into the ring and its mirror; `pos`/`pos_off` anchor the mapping
- * (to - (pos & ~3) <= R). */
+ * (to - (pos & ~3) <= R).  Bytes at or past n arrive as zeros. */
 template <int G>
 __device__ __forceinline__ void ring_issue(const Ring rg, const float *__restrict__ x, unsigned n,
 	unsigned pos, unsigned pos_off, unsigned from, unsigned to, unsigned g)
 {
-    unsigned i = from + 4u * g;
-    if (i >= to)
+    if (to <= from)
 	return;
-    /* ring offset of absolute index i: pos_off + (i - pos), i - pos >= -3 */
-    int off0 = (int)pos_off + (int)(i - pos);
+    int off0 = (int)pos_off + (int)(from - pos);	/* from - pos >= -3 */
     if (off0 < 0)
 	off0 += (int)rg.R;
     unsigned off = (unsigned)off0;
     if (off >= rg.R)
 	off -= rg.R;
     const unsigned ring_s = (unsigned)__cvta_generic_to_shared(rg.ring);
-    const float *src = x + i;
-    for (; i < to; i += 4u * G, src += 4 * G) {
-	const unsigned valid = i + 4u <= n ? 16u : (i < n ? (n - i) * 4u : 0u);
-	const float *s = valid ? src : x;
-	asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n"
-		:: "r"(ring_s + off * 4u), "l"(s), "r"(valid) : "memory");
+    if (to <= n) {
+	/* whole range valid: at most two linear runs plus their mirrored heads */
+	const unsigned len = to - from;
+	const unsigned run1 = min(len, rg.R - off), run2 = len - run1;
+	ring_run<G>(ring_s + off * 4u, x + from, run1, g);
+	if (run2)
+	    ring_run<G>(ring_s, x + from + run1, run2, g);
 	if (off < rg.pad)
-	    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n"
-		    :: "r"(ring_s + (rg.R + off) * 4u), "l"(s), "r"(valid) : "memory");
+	    ring_run<G>(ring_s + (rg.R + off) * 4u, x + from, min(run1, rg.pad - off), g);
+	if (run2)
+	    ring_run<G>(ring_s + rg.R * 4u, x + from + run1, min(run2, rg.pad), g);
+	return;
+    }
+    /* end of the stream: per-chunk validity, zero fill */
+    unsigned i = from + 4u * g;
+    off += 4u * g;
+    if (off >= rg.R)
+	off -= rg.R;
+    for (; i < to; i += 4u * G) {
+	const unsigned valid = i + 4u <= n ? 16u : (i < n ? (n - i) * 4u : 0u);
+	const float *s = valid ? x + i : x;
+	ldgsts16_zfill(ring_s + off * 4u, s, valid);
+	if (off < rg.pad)
+	    ldgsts16_zfill(ring_s + (rg.R + off) * 4u, s, valid);
 	off += 4u * G;
 	if (off >= rg.R)
 	    off -= rg.R;
+    }
+}
+
+/* ------------------------------------------------------------------------ */
+/* ring fill through the TMA engine: cp.async.bulk (global -> shared, 1-D),  */
+/* completion counted in bytes on a per-stream mbarrier                      */
+/* ------------------------------------------------------------------------ */
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity)
+{
+    unsigned ok;
+    asm volatile("{\n.reg .pred p;\n"
+	    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+	    "selp.u32 %0, 1, 0, p;\n}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+/* bounded spin: a byte-count bug must end in a trapped kernel, never a hung GPU */
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
+{
+    for (unsigned spin = 0; !mbar_try_wait(bar, parity); spin++)
+	if (spin > (1u << 24))
+	    __trap();
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+	    :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+/* Lane 0 of the group copies absolute indices [from, to) (multiples of 4, to <= the
+ * 4-rounded valid length, to - (pos & ~3) <= R) into the ring and its mirror with at
+ * most four bulk copies (the range may wrap the ring once; the part that falls into
+ * the first `pad` floats is copied to the mirror as well) and arms `bar` with the
+ * byte count.  Called exactly once per barrier phase, possibly with an empty range. */
+__device__ __forceinline__ void ring_issue_bulk(const Ring rg, const float *__restrict__ x,
+	unsigned pos, unsigned pos_off, unsigned from, unsigned to, unsigned bar)
+{
+    const unsigned len = to > from ? to - from : 0u;
+    const unsigned ring_s = smem_u32(rg.ring);
+    int off0 = (int)pos_off + (int)(from - pos);
+    if (off0 < 0)
+	off0 += (int)rg.R;
+    unsigned off = (unsigned)off0;
+    if (off >= rg.R)
+	off -= rg.R;
+    /* main copy: up to two runs */
+    const unsigned run1 = min(len, rg.R - off), run2 = len - run1;
+    /* mirror: the parts of the runs below `pad` */
+    const unsigned m1 = off < rg.pad ? min(run1, rg.pad - off) : 0u;	/* run1 starts at off */
+    const unsigned m2 = min(run2, rg.pad);				/* run2 starts at 0 */
+    mbar_arrive_expect_tx(bar, (run1 + run2 + m1 + m2) * 4u);
+    if (run1)
+	bulk_g2s(ring_s + off * 4u, x + from, run1 * 4u, bar);
+    if (run2)
+	bulk_g2s(ring_s, x + from + run1, run2 * 4u, bar);
+    if (m1)
+	bulk_g2s(ring_s + (rg.R + off) * 4u, x + from, m1 * 4u, bar);
+    if (m2)
+	bulk_g2s(ring_s + rg.R * 4u, x + from + run1, m2 * 4u, bar);
+}
+
+/* plain zero fill of absolute indices [from, to) (any alignment) by the group */
+template <int G>
+__device__ __forceinline__ void ring_zero(const Ring rg, unsigned pos, unsigned pos_off,
+	unsigned from, unsigned to, unsigned g)
+{
+    for (unsigned i = from + g; i < to; i += G) {
+	int off0 = (int)pos_off + (int)(i - pos);
+	if (off0 < 0)
+	    off0 += (int)rg.R;
+	unsigned off = (unsigned)off0;
+	if (off >= rg.R)
+	    off -= rg.R;
+	rg.ring[off] = 0.f;
+	if (off < rg.pad)
+	    rg.ring[rg.R + off] = 0.f;
     }
 }
 

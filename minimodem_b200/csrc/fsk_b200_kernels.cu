@@ -42,11 +42,13 @@ static unsigned long long g_launches;
 /* ------------------------------------------------------------------------ */
 /* shared memory carve-up                                                   */
 /* ------------------------------------------------------------------------ */
-/* [twiddles: N float4 (optional)] [rings: slots x (ring_floats + pad)] [scratch: slots x n_bits float2] */
+/* [twiddles: N float4 (optional)] [rings: slots x (ring_floats + pad)] [scratch: slots x n_bits float2]
+ * [mbarriers: slots x 2 x u64] */
 struct Smem {
     const float4 *tw;
     float *ring;
     float2 *scr;
+    unsigned long long *bars;	/* two mbarriers per stream (bulk fill) */
 };
 
 template <int G>
@@ -71,6 +73,7 @@ __device__ __forceinline__ Smem carve(float4 *smem, const fsk_b200_geom &geo,
     s.ring = rings + (size_t)slot * (ring_floats + pad);
     float2 *scrs = reinterpret_cast<float2 *>(rings + (size_t)wpb * spw * (ring_floats + pad));
     s.scr = scrs + (size_t)slot * geo.n_bits;
+    s.bars = reinterpret_cast<unsigned long long *>(scrs + (size_t)wpb * spw * geo.n_bits) + 2 * slot;
     __syncthreads();
     return s;
 }
@@ -157,7 +160,9 @@ k_find_frame(const __grid_constant__ fsk_b200_geom geo, const float4 *__restrict
 /* K2: the rx loop (src/minimodem.c:1137-1463) for whole streams            */
 /* ------------------------------------------------------------------------ */
 
-template <int G, int W, int L, int MODE>
+/* FILL 0: cp.async (LDGSTS) by all lanes of the group; FILL 1: cp.async.bulk (TMA engine)
+ * issued by lane 0 with mbarrier completion */
+template <int G, int W, int L, int MODE, int FILL>
 __global__ void __launch_bounds__(128, 4)
 k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200_loopc lc,
 	const float4 *__restrict__ tw_global, unsigned tw_in_smem, unsigned ring_floats,
@@ -188,16 +193,87 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
 	unsigned done = 0;
 
 	/* ring bookkeeping (MODE 0): ring offset of `pos`, and the absolute index up to
-	 * which copies have been ISSUED */
+	 * which the ring content has been REQUESTED (copies issued or zeros stored) */
 	unsigned pos_off = pos & 3u;
 	unsigned filled = pos & ~3u;
 	const unsigned need_max = lc.try_max_nocarrier - 1u + geo.span;
-	if (MODE == 0) {
+	const unsigned n4 = (n + 3u) & ~3u;		/* rows are readable up to a multiple of 4 */
+	const unsigned bar0 = smem_u32(sm.bars), bar1 = bar0 + 8u;
+	unsigned kphase = 0;				/* bulk fill: number of barrier phases armed */
+	bool tail_fix = false;				/* bulk fill: [n, n4) holds row padding, not zeros */
+
+	/* request [filled, to): returns true if anything was requested */
+	auto request = [&](unsigned to) {
+	    if (FILL == 0) {
+		if (to > filled)
+		    ring_issue<G>(rg, x, n, pos, pos_off, filled, to, g);
+		cp_async_commit();
+	    } else {
+		const unsigned to_b = min(to, n4);
+		const unsigned from_b = min(filled, to_b);
+		if (g == 0)
+		    ring_issue_bulk(rg, x, pos, pos_off, from_b, to_b, (kphase & 1u) ? bar1 : bar0);
+		if (n < n4 && from_b < n4 && to_b == n4 && to_b > from_b)
+		    tail_fix = true;
+		kphase++;
+		if (to > max(filled, n4))		/* past the end of the stream: zeros */
+		    ring_zero<G>(rg, pos, pos_off, max(filled, n4), to, g);
+	    }
+	    if (to > filled)
+		filled = to;
+	};
+	/* wait for everything requested before the latest request (all of it if `all`) */
+	auto settle = [&](bool all) {
+	    if (FILL == 0) {
+		if (all)
+		    cp_async_wait<0>();
+		else
+		    cp_async_wait<1>();
+	    } else {
+		/* phase k (0-based) lives on barrier k&1 with parity (k>>1)&1 */
+		if (kphase >= 2u) {
+		    const unsigned k = kphase - 2u;
+		    mbar_wait((k & 1u) ? bar1 : bar0, (k >> 1) & 1u);
+		}
+		if ((all || tail_fix) && kphase >= 1u) {
+		    const unsigned k = kphase - 1u;
+		    mbar_wait((k & 1u) ? bar1 : bar0, (k >> 1) & 1u);
+		}
+		if (tail_fix) {
+		    __syncwarp(gmask);
+		    if (n >= (pos & ~3u))
+			ring_zero<G>(rg, pos, pos_off, n, n4, g);
+		    tail_fix = false;
+		}
+	    }
 	    __syncwarp(gmask);
-	    const unsigned to = min((pos + need_max + 3u) & ~3u, (pos & ~3u) + R);
-	    ring_issue<G>(rg, x, n, pos, pos_off, filled, to, g);
-	    cp_async_commit();
-	    filled = to;
+	};
+	/* wait until nothing is in flight into this ring */
+	auto drain = [&]() {
+	    if (FILL == 0) {
+		cp_async_wait<0>();
+	    } else {
+		if (kphase >= 2u) {
+		    const unsigned k = kphase - 2u;
+		    mbar_wait((k & 1u) ? bar1 : bar0, (k >> 1) & 1u);
+		}
+		if (kphase >= 1u) {
+		    const unsigned k = kphase - 1u;
+		    mbar_wait((k & 1u) ? bar1 : bar0, (k >> 1) & 1u);
+		}
+	    }
+	    __syncwarp(gmask);
+	};
+	if (MODE == 0) {
+	    if (FILL == 1) {
+		if (g == 0) {
+		    mbar_init(bar0, 1);
+		    mbar_init(bar1, 1);
+		    mbar_fence_init();
+		}
+	    }
+	    __syncwarp(gmask);
+	    request(min((pos + need_max + 3u) & ~3u, (pos & ~3u) + R));
 	}
 
 	for (;;) {
@@ -218,18 +294,9 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
 		/* prefetch what the NEXT iteration can need (it starts at most `lookahead`
 		 * samples further), then wait only for what THIS one needs */
 		const unsigned need_now = (pos + try_max - 1u + geo.span + 3u) & ~3u;
-		const unsigned to = min((pos + lookahead + need_max + 3u) & ~3u, (pos & ~3u) + R);
 		const bool late = filled < need_now;	/* part of this window is only now requested */
-		if (to > filled) {
-		    ring_issue<G>(rg, x, n, pos, pos_off, filled, to, g);
-		    filled = to;
-		}
-		cp_async_commit();
-		if (late)
-		    cp_async_wait<0>();
-		else
-		    cp_async_wait<1>();
-		__syncwarp(gmask);
+		request(min((pos + lookahead + need_max + 3u) & ~3u, (pos & ~3u) + R));
+		settle(late);
 	    }
 	    const GlobalSrc gsrc = { x, n };
 
@@ -322,7 +389,7 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
 		pos_off = ring_wrap(pos_off + advance, R);	/* advance < R by construction */
 		if (filled < (pos & ~3u)) {
 		    /* skipped past everything requested so far: restart the ring here */
-		    cp_async_wait<0>();
+		    drain();
 		    filled = pos & ~3u;
 		    pos_off = pos & 3u;
 		}
@@ -330,7 +397,7 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
 	    }
 	}
 	if (MODE == 0)
-	    cp_async_wait<0>();		/* nothing in flight into this ring slot when it is reused */
+	    drain();	/* before the slot is reused or the block exits */
 
 	if (g == 0) {
 	    st.pos = pos;
@@ -460,7 +527,7 @@ struct CudaEngine {
     int tw_fftsize;
     unsigned tw_bm, tw_bs;
     /* tuning (0 = automatic) */
-    int lanes, wpb, ring, split;
+    int lanes, wpb, ring, split, fill;
     /* single-stream staging */
     float *d_one;
     size_t d_one_cap;
@@ -505,6 +572,8 @@ extern "C" void *fsk_b200_cuda_engine_new(void)
     if ((e = getenv("FSK_B200_WPB"))) ce->wpb = atoi(e);
     if ((e = getenv("FSK_B200_RING"))) ce->ring = atoi(e);
     if ((e = getenv("FSK_B200_SPLIT"))) ce->split = atoi(e);
+    ce->fill = 0;		/* cp.async (LDGSTS) by all lanes; FSK_B200_FILL=1 selects TMA bulk copies */
+    if ((e = getenv("FSK_B200_FILL"))) ce->fill = atoi(e) ? 1 : 0;
     return ce;
 }
 
@@ -656,7 +725,7 @@ static int pick_shape(const CudaEngine *ce, const fsk_b200_geom *g, unsigned nee
     sh->tw_in_smem = tw_bytes <= 24 * 1024;
     const size_t fixed = sh->tw_in_smem ? tw_bytes : 0;
     const size_t pad_bytes = (size_t)((g->bit_nsamples + 3u) & ~3u) * 4;
-    const size_t scr_bytes = (size_t)g->n_bits * sizeof(float2) + pad_bytes;	/* per stream, besides the ring */
+    const size_t scr_bytes = (size_t)g->n_bits * sizeof(float2) + pad_bytes + 16;	/* per stream, besides the ring: scratch, mirror, 2 mbarriers */
 
     /* ring: the widest search window plus (ideally) one full advance of look-ahead */
     const unsigned ring_min = (need_floats + 8u + 3u) & ~3u;
@@ -706,7 +775,7 @@ static int pick_shape(const CudaEngine *ce, const fsk_b200_geom *g, unsigned nee
 	}
 	if (ring) { ring = 0; fast = false; continue; }	/* not even one ring fits: read global memory */
 	sh->tw_in_smem = 0;
-	sh->smem = ((size_t)g->n_bits * sizeof(float2) + 15) & ~(size_t)15;
+	sh->smem = ((size_t)g->n_bits * sizeof(float2) + 16 + 15) & ~(size_t)15;
 	break;
     }
     if (!fast) {
@@ -718,7 +787,7 @@ static int pick_shape(const CudaEngine *ce, const fsk_b200_geom *g, unsigned nee
 	    L *= 2;
 	W = (int)((g->n_bits + 32 / L - 1) / (32 / L));
 	const size_t fixed2 = sh->tw_in_smem ? tw_bytes : 0;
-	const size_t scr_only = (size_t)g->n_bits * sizeof(float2);
+	const size_t scr_only = (size_t)g->n_bits * sizeof(float2) + 16;
 	wpb = ce->wpb ? ce->wpb : 4;
 	sh->smem = (fixed2 + (size_t)wpb * scr_only + 15) & ~(size_t)15;
 	if (sh->smem > smem_max) {
@@ -789,15 +858,15 @@ extern "C" int fsk_b200_cuda_find_frame_batch(void *p, const fsk_b200_geom *g, c
     return 0;
 }
 
-template <int G, int W, int L, int MODE>
+template <int G, int W, int L, int MODE, int FILL>
 static cudaError_t launch_rx_t(const Shape &sh, const CudaEngine *ce, const fsk_b200_loopc *lc,
 	const RxArgs &a, cudaStream_t st)
 {
-    cudaError_t e = cudaFuncSetAttribute(k_rx<G, W, L, MODE>,
+    cudaError_t e = cudaFuncSetAttribute(k_rx<G, W, L, MODE, FILL>,
 	    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh.smem);
     if (e != cudaSuccess)
 	return e;
-    k_rx<G, W, L, MODE><<<sh.blocks, sh.wpb * 32, sh.smem, st>>>(sh.geo, *lc, ce->d_tw, sh.tw_in_smem,
+    k_rx<G, W, L, MODE, FILL><<<sh.blocks, sh.wpb * 32, sh.smem, st>>>(sh.geo, *lc, ce->d_tw, sh.tw_in_smem,
 	    sh.ring, sh.lookahead, a);
     g_launches++;
     return cudaGetLastError();
@@ -823,11 +892,17 @@ extern "C" int fsk_b200_cuda_rx_batch(void *p, const fsk_b200_geom *g, const fsk
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e = cudaErrorInvalidValue;
     if (sh.mode == 0) {
-#define X(GG, WW, LL) if (sh.G == GG && sh.W == WW && sh.L == LL) e = launch_rx_t<GG, WW, LL, 0>(sh, ce, lc, a, st);
-	FAST_COMBOS(X)
+	if (ce->fill == 0) {
+#define X(GG, WW, LL) if (sh.G == GG && sh.W == WW && sh.L == LL) e = launch_rx_t<GG, WW, LL, 0, 0>(sh, ce, lc, a, st);
+	    FAST_COMBOS(X)
 #undef X
+	} else {
+#define X(GG, WW, LL) if (sh.G == GG && sh.W == WW && sh.L == LL) e = launch_rx_t<GG, WW, LL, 0, 1>(sh, ce, lc, a, st);
+	    FAST_COMBOS(X)
+#undef X
+	}
     } else {
-	e = launch_rx_t<32, 1, 1, 1>(sh, ce, lc, a, st);
+	e = launch_rx_t<32, 1, 1, 1, 0>(sh, ce, lc, a, st);
     }
     if (e != cudaSuccess) {
 	fsk_b200_set_error("rx_batch launch (G=%d W=%d L=%d mode=%d ring=%u smem=%zu): %s", sh.G, sh.W,
