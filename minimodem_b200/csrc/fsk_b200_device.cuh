@@ -433,7 +433,7 @@ __device__ __forceinline__ float frame_analyze_fast(const Ring rg, unsigned cand
 }
 
 template <int G, int W, int L>
-__device__ __forceinline__ float find_frame_fast(const Ring rg, unsigned pos_off,
+__device__ __noinline__ float find_frame_fast(const Ring rg, unsigned pos_off,
 	const fsk_b200_geom &geo, int sel, const float4 *__restrict__ tw,
 	unsigned g, unsigned gmask, unsigned try_first, unsigned try_max, unsigned try_step,
 	float limit, unsigned long long &best_bits, float &best_a, unsigned &best_t)
@@ -517,6 +517,50 @@ __device__ __forceinline__ void ring_issue(const Ring rg, const float *__restric
 	off += 4u * G;
 	if (off >= rg.R)
 	    off -= rg.R;
+    }
+}
+
+
+/* Block-granular fill: the ring is filled in blocks of RING_BLOCK floats that never
+ * wrap (R % RING_BLOCK == 0 and blocks start at multiples of RING_BLOCK from the ring
+ * origin), so every lane issues exactly 32/G 16-byte copies per block with immediate
+ * offsets -- no per-chunk address arithmetic, no remainder loops. */
+#define RING_BLOCK 128u
+
+/* one whole block, all of it valid: foff = ring offset of the block, src = its first sample */
+template <int G>
+__device__ __forceinline__ void ring_block(const Ring rg, unsigned ring_s, unsigned foff,
+	const float *__restrict__ src, unsigned g)
+{
+    constexpr int CPL = 32 / G;			/* copies per lane */
+    const unsigned d = ring_s + (foff + 4u * g) * 4u;
+    const float *sp = src + 4u * g;
+#pragma unroll
+    for (int k = 0; k < CPL; k++)
+	ldgsts16(d + (unsigned)k * 16u * G, sp + k * 4 * G);
+    if (foff < rg.pad) {			/* the head of the ring is mirrored behind its end */
+#pragma unroll
+	for (int k = 0; k < CPL; k++)
+	    if (foff + 4u * (g + (unsigned)k * G) < rg.pad)
+		ldgsts16(d + rg.R * 4u + (unsigned)k * 16u * G, sp + k * 4 * G);
+    }
+}
+
+/* a block that reaches past the valid length n: bytes at or past n arrive as zeros */
+template <int G>
+__device__ __forceinline__ void ring_block_tail(const Ring rg, unsigned ring_s, unsigned foff,
+	const float *__restrict__ x, unsigned n, unsigned first, unsigned g)
+{
+    constexpr int CPL = 32 / G;
+#pragma unroll
+    for (int k = 0; k < CPL; k++) {
+	const unsigned c = 4u * (g + (unsigned)k * G);
+	const unsigned i = first + c;
+	const unsigned valid = i + 4u <= n ? 16u : (i < n ? (n - i) * 4u : 0u);
+	const float *sp = valid ? x + i : x;
+	ldgsts16_zfill(ring_s + (foff + c) * 4u, sp, valid);
+	if (foff + c < rg.pad)
+	    ldgsts16_zfill(ring_s + (rg.R + foff + c) * 4u, sp, valid);
     }
 }
 

@@ -202,11 +202,22 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
 	unsigned kphase = 0;				/* bulk fill: number of barrier phases armed */
 	bool tail_fix = false;				/* bulk fill: [n, n4) holds row padding, not zeros */
 
-	/* request [filled, to): returns true if anything was requested */
+	const unsigned ring_s = smem_u32(rg.ring);
+	unsigned foff = 0;				/* block fill: ring offset of `filled` */
+	/* request the ring content up to absolute index `to` (rounded up to whole blocks) */
 	auto request = [&](unsigned to) {
 	    if (FILL == 0) {
-		if (to > filled)
-		    ring_issue<G>(rg, x, n, pos, pos_off, filled, to, g);
+		const unsigned cap = (pos & ~3u) + R;
+		while (filled < to && filled + RING_BLOCK <= cap) {
+		    if (filled + RING_BLOCK <= n)
+			ring_block<G>(rg, ring_s, foff, x + filled, g);
+		    else
+			ring_block_tail<G>(rg, ring_s, foff, x, n, filled, g);
+		    filled += RING_BLOCK;
+		    foff += RING_BLOCK;
+		    if (foff >= R)
+			foff = 0;
+		}
 		cp_async_commit();
 	    } else {
 		const unsigned to_b = min(to, n4);
@@ -218,9 +229,9 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
 		kphase++;
 		if (to > max(filled, n4))		/* past the end of the stream: zeros */
 		    ring_zero<G>(rg, pos, pos_off, max(filled, n4), to, g);
+		if (to > filled)
+		    filled = to;
 	    }
-	    if (to > filled)
-		filled = to;
 	};
 	/* wait for everything requested before the latest request (all of it if `all`) */
 	auto settle = [&](bool all) {
@@ -392,6 +403,7 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
 		    drain();
 		    filled = pos & ~3u;
 		    pos_off = pos & 3u;
+		    foff = 0;
 		}
 		__syncwarp(gmask);	/* every read of this window precedes the next copies */
 	    }
@@ -604,8 +616,8 @@ extern "C" int fsk_b200_cuda_tune(void *p, int lanes, int wpb, int ring)
 	fsk_b200_set_error("lanes per stream must be 4, 8, 16 or 32");
 	return -EINVAL;
     }
-    if (ring && (ring < 64 || (ring & 3))) {
-	fsk_b200_set_error("ring size must be a multiple of 4 floats, >= 64");
+    if (ring && ring < 128) {
+	fsk_b200_set_error("ring size must be at least 128 floats (it is rounded up to whole 128-float blocks)");
 	return -EINVAL;
     }
     if (wpb < 0 || wpb > 4) {
@@ -728,16 +740,18 @@ static int pick_shape(const CudaEngine *ce, const fsk_b200_geom *g, unsigned nee
     const size_t scr_bytes = (size_t)g->n_bits * sizeof(float2) + pad_bytes + 16;	/* per stream, besides the ring: scratch, mirror, 2 mbarriers */
 
     /* ring: the widest search window plus (ideally) one full advance of look-ahead */
-    const unsigned ring_min = (need_floats + 8u + 3u) & ~3u;
-    unsigned ring = ce->ring ? (((unsigned)ce->ring + 3u) & ~3u) : ((need_floats + max_advance + 8u + 3u) & ~3u);
+    /* whole blocks; room for the widest window starting anywhere inside a block */
+    const unsigned ring_min = (need_floats + 8u + 2u * RING_BLOCK - 1u) / RING_BLOCK * RING_BLOCK;
+    (void)max_advance;
+    /* default: the minimum, which already leaves 1..2 blocks of look-ahead (measured: deeper
+     * rings do not pay, fewer resident streams do cost) */
+    unsigned ring = ce->ring ? ((unsigned)ce->ring + RING_BLOCK - 1u) / RING_BLOCK * RING_BLOCK : ring_min;
     if (ring < ring_min)
 	ring = ring_min;
     /* keep at least ~24 streams per SM resident if that is possible at all */
     if (!ce->ring) {
 	while (ring > ring_min && (smem_max - fixed) / ((size_t)ring * 4 + scr_bytes) < 24)
-	    ring = (ring_min + ring) / 2 & ~3u;
-	if (ring < ring_min)
-	    ring = ring_min;
+	    ring -= RING_BLOCK;
     }
 
     int G = ce->lanes;
@@ -747,7 +761,7 @@ static int pick_shape(const CudaEngine *ce, const fsk_b200_geom *g, unsigned nee
 	if (streams_per_sm < 1)
 	    streams_per_sm = 1;
 	G = 8;
-	while (G < 32 && streams_per_sm * (size_t)G < 512)
+	while (G < 32 && streams_per_sm * (size_t)G < 256)
 	    G <<= 1;
     }
     int W = 1, L = 1;
@@ -801,7 +815,11 @@ static int pick_shape(const CudaEngine *ce, const fsk_b200_geom *g, unsigned nee
     sh->L = L;
     sh->wpb = wpb;
     sh->ring = ring;
-    sh->lookahead = ring > ring_min ? (ring - ring_min < max_advance ? ring - ring_min : max_advance) : 0;
+    {
+	const unsigned base_need = need_floats + 8u + RING_BLOCK;
+	const unsigned slack = ring > base_need ? ring - base_need : 0u;
+	sh->lookahead = slack < max_advance ? slack : max_advance;
+    }
     sh->geo.lanes_per_window = (unsigned)L;
     /* one block per wpb*(32/G) streams: the hardware block scheduler hands out
      * streams as SM resources free up (streams differ in length and work) */
