@@ -208,15 +208,11 @@ def run_ours(a):
         dist.init_process_group("nccl", device_id=dev)
 
     # ---- plan: derived on rank 0, broadcast over NCCL (the only collective on the path)
-    nbytes = C.sizeof(mm.RxParams)
-    blob = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
     cfg = mm.rx_config_for_mode(a.mode, a.rate)
-    if rank == 0:
-        p0 = mm.rx_params(cfg)
-        blob.copy_(torch.frombuffer(bytearray(bytes(p0)), dtype=torch.uint8))
+    params = mm.rx_params(cfg)
     if world > 1:
-        dist.broadcast(blob, src=0)
-    params = mm.RxParams.from_buffer_copy(bytes(blob.cpu().numpy().tobytes()))
+        from minimodem_b200 import dist as mdist
+        params = mdist.broadcast_params(params if rank == 0 else None, src=0, device=dev)
     eng = mm.RxEngine(params)
     if a.lanes or a.wpb or a.ring:
         eng.tune(a.lanes, a.wpb, a.ring)
