@@ -205,6 +205,8 @@ def run_ours(a):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+            os.environ["NCCL_DEBUG"] = "ERROR"      # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     # ---- plan: derived on rank 0, broadcast over NCCL (the only collective on the path)

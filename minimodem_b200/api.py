@@ -17,7 +17,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfsk_b200.so")
+LIB_PATH = os.environ.get("FSK_B200_LIB") or os.path.join(_HERE, "libfsk_b200.so")   # override: tuning builds
 MAX_BITS = 64
 FRAME_ACQUIRED = 0x80000000
 FRAME_REPORT = 0xFFFFFFFF

@@ -268,6 +268,17 @@ struct Ring {
 
 __device__ __forceinline__ unsigned ring_wrap(unsigned off, unsigned R) { return off >= R ? off - R : off; }
 
+/* Fast-path arithmetic: sqrt.approx / div.approx (<= 2 ulp) instead of the IEEE sequences.
+ * They feed magnitudes and the confidence statistic, which are compared to tolerance; the
+ * generic path keeps IEEE operations. */
+__device__ __forceinline__ float fast_sqrt(float x)
+{
+    float r;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float fast_div(float a, float b) { return __fdividef(a, b); }
+
 /* butterfly all-reduce over the G lanes of a group (every lane ends with the total) */
 template <int G>
 __device__ __forceinline__ float group_sum(float v, unsigned gmask)
@@ -323,7 +334,13 @@ __device__ __forceinline__ float frame_analyze_fast(const Ring rg, unsigned cand
     for (int j = 0; j < W; j++)
 	acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
 
-#pragma unroll 4
+#if defined(FSK_UNROLL) && FSK_UNROLL == 8
+    _Pragma("unroll 8")
+#elif defined(FSK_UNROLL) && FSK_UNROLL == 2
+    _Pragma("unroll 2")
+#else
+    _Pragma("unroll 4")
+#endif
     for (unsigned n = part; n < N; n += L) {
 	const float4 c = tw[n];
 #pragma unroll
@@ -360,8 +377,8 @@ __device__ __forceinline__ float frame_analyze_fast(const Ring rg, unsigned cand
 	sig[j] = 0.f;
 	one[j] = false;
 	if (own[j]) {
-	    float mag_mark = sqrtf(acc[j][0] * acc[j][0] + acc[j][1] * acc[j][1]) * geo.mag_scalar;
-	    float mag_space = sqrtf(acc[j][2] * acc[j][2] + acc[j][3] * acc[j][3]) * geo.mag_scalar;
+	    float mag_mark = fast_sqrt(acc[j][0] * acc[j][0] + acc[j][1] * acc[j][1]) * geo.mag_scalar;
+	    float mag_space = fast_sqrt(acc[j][2] * acc[j][2] + acc[j][3] * acc[j][3]) * geo.mag_scalar;
 	    if (needs_resum(mag_mark, mag_space)) {
 		const float *q = p[j];
 		double drm = 0., dim = 0., drs = 0., dis = 0.;
@@ -409,23 +426,23 @@ __device__ __forceinline__ float frame_analyze_fast(const Ring rg, unsigned cand
 	bhi = group_or<G>(bhi, gmask);
 
     const unsigned n_space = nb - nm;
-    const float snr = ts / tn;					/* :292, may be +inf */
-    const float avg_bit_sig = ts / (float)(int)nb;		/* :295 */
+    const float snr = fast_div(ts, tn);					/* :292, may be +inf */
+    const float avg_bit_sig = fast_div(ts, (float)(int)nb);		/* :295 */
     if (nm)
-	am = am / (float)nm;					/* :298-301 */
+	am = fast_div(am, (float)nm);					/* :298-301 */
     if (n_space)
-	as = as / (float)n_space;
+	as = fast_div(as, (float)n_space);
     float dv = 0.f;						/* :305-311 */
 #pragma unroll
     for (int j = 0; j < W; j++) {
 	if (own[j]) {
 	    const float other = one[j] ? am : as;
-	    dv += fabsf(sig[j] - other) / other;
+	    dv += fast_div(fabsf(sig[j] - other), other);
 	}
     }
     float divergence = group_sum<G>(dv, gmask);
     divergence *= 2.f;						/* :312-313 */
-    divergence = divergence / (float)(int)nb;
+    divergence = fast_div(divergence, (float)(int)nb);
 
     bits_out = ((unsigned long long)bhi << 32) | blo;
     ampl_out = avg_bit_sig;					/* :342 */
@@ -525,14 +542,18 @@ __device__ __forceinline__ void ring_issue(const Ring rg, const float *__restric
  * wrap (R % RING_BLOCK == 0 and blocks start at multiples of RING_BLOCK from the ring
  * origin), so every lane issues exactly 32/G 16-byte copies per block with immediate
  * offsets -- no per-chunk address arithmetic, no remainder loops. */
+#ifdef FSK_RING_BLOCK
+#define RING_BLOCK FSK_RING_BLOCK
+#else
 #define RING_BLOCK 128u
+#endif
 
 /* one whole block, all of it valid: foff = ring offset of the block, src = its first sample */
 template <int G>
 __device__ __forceinline__ void ring_block(const Ring rg, unsigned ring_s, unsigned foff,
 	const float *__restrict__ src, unsigned g)
 {
-    constexpr int CPL = 32 / G;			/* copies per lane */
+    constexpr int CPL = (int)(RING_BLOCK / 4u) / G;	/* copies per lane */
     const unsigned d = ring_s + (foff + 4u * g) * 4u;
     const float *sp = src + 4u * g;
 #pragma unroll
@@ -551,7 +572,7 @@ template <int G>
 __device__ __forceinline__ void ring_block_tail(const Ring rg, unsigned ring_s, unsigned foff,
 	const float *__restrict__ x, unsigned n, unsigned first, unsigned g)
 {
-    constexpr int CPL = 32 / G;
+    constexpr int CPL = (int)(RING_BLOCK / 4u) / G;
 #pragma unroll
     for (int k = 0; k < CPL; k++) {
 	const unsigned c = 4u * (g + (unsigned)k * G);

@@ -163,7 +163,10 @@ k_find_frame(const __grid_constant__ fsk_b200_geom geo, const float4 *__restrict
 /* FILL 0: cp.async (LDGSTS) by all lanes of the group; FILL 1: cp.async.bulk (TMA engine)
  * issued by lane 0 with mbarrier completion */
 template <int G, int W, int L, int MODE, int FILL>
-__global__ void __launch_bounds__(128, 4)
+#ifndef FSK_MINBLOCKS
+#define FSK_MINBLOCKS 4
+#endif
+__global__ void __launch_bounds__(128, FSK_MINBLOCKS)
 k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200_loopc lc,
 	const float4 *__restrict__ tw_global, unsigned tw_in_smem, unsigned ring_floats,
 	unsigned lookahead, const __grid_constant__ RxArgs a)
@@ -690,12 +693,16 @@ struct Shape {
 
 /* (G, W, L) combinations that are instantiated for the fast path: G lanes per
  * stream, L lanes per bit window, W windows per lane (W * G/L >= n_bits) */
+#ifdef FSK_EXPERIMENT		/* quick builds for tuning runs */
+#define FAST_COMBOS(X) X(8, 3, 2) X(8, 2, 1) X(4, 3, 1) X(16, 3, 4) X(8, 1, 1) X(8, 2, 2)
+#else
 #define FAST_COMBOS(X) \
     X(4, 1, 1) X(4, 2, 1) X(4, 3, 1) X(4, 4, 1) X(4, 2, 2) X(4, 4, 2) \
     X(8, 1, 1) X(8, 2, 1) X(8, 3, 1) X(8, 4, 1) X(8, 1, 2) X(8, 2, 2) X(8, 3, 2) X(8, 4, 2) X(8, 4, 4) \
     X(16, 1, 1) X(16, 2, 1) X(16, 3, 1) X(16, 4, 1) X(16, 1, 2) X(16, 2, 2) X(16, 3, 2) X(16, 4, 2) \
     X(16, 1, 4) X(16, 2, 4) X(16, 3, 4) X(16, 4, 4) \
     X(32, 1, 1) X(32, 2, 1) X(32, 1, 2) X(32, 2, 2) X(32, 3, 2) X(32, 4, 2) X(32, 1, 4) X(32, 2, 4) X(32, 3, 4) X(32, 4, 4)
+#endif
 
 static bool fast_combo(int G, int W, int L)
 {
