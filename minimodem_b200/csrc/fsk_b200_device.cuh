@@ -262,7 +262,7 @@ __device__ __forceinline__ float find_frame(const Src &src, unsigned base,
  * absolute sample index `pos` (pos_off == pos mod 4 is kept, so the 16-byte
  * chunks of the stream line up with 16-byte chunks of the ring). */
 struct Ring {
-    float *ring;
+    unsigned ring_s;		/* shared-window address of the ring */
     unsigned R, pad;
 };
 
@@ -313,9 +313,14 @@ __device__ __forceinline__ unsigned group_add(unsigned v, unsigned gmask)
  * (same terms, different but fixed summation order). */
 template <int G, int W, int L>
 __device__ __forceinline__ float frame_analyze_fast(const Ring rg, unsigned cand_off,
-	const fsk_b200_geom &geo, int sel, const float4 *__restrict__ tw,
+	const fsk_b200_geom &geo, int sel, unsigned tw_s,
 	unsigned g, unsigned gmask, unsigned long long &bits_out, float &ampl_out)
 {
+    /* ring and twiddles are handed over as shared-window addresses and turned back into
+     * pointers here, so that the compiler keeps them in the shared address space (LDS with
+     * 32-bit addresses and immediate offsets) even though this code is not inlined */
+    const float *ring = static_cast<const float *>(__cvta_shared_to_generic(rg.ring_s));
+    const float4 *tw = static_cast<const float4 *>(__cvta_shared_to_generic(tw_s));
     /* cand_off: ring offset (< R) of the candidate's first sample */
     constexpr unsigned WPP = G / L;		/* windows per pass */
     const unsigned N = geo.bit_nsamples, nb = geo.n_bits, R = rg.R;
@@ -326,7 +331,7 @@ __device__ __forceinline__ float frame_analyze_fast(const Ring rg, unsigned cand
 #pragma unroll
     for (int j = 0; j < W; j++) {
 	const unsigned w = j * WPP + wslot;
-	p[j] = rg.ring + ring_wrap(cand_off + (w < nb ? geo.bit_begin[w] : 0u), R);
+	p[j] = ring + ring_wrap(cand_off + (w < nb ? geo.bit_begin[w] : 0u), R);
     }
 
     float acc[W][4];
@@ -382,6 +387,7 @@ __device__ __forceinline__ float frame_analyze_fast(const Ring rg, unsigned cand
 	    if (needs_resum(mag_mark, mag_space)) {
 		const float *q = p[j];
 		double drm = 0., dim = 0., drs = 0., dis = 0.;
+#pragma unroll 1
 		for (unsigned i = 0; i < N; i++) {
 		    const double x = (double)q[i];
 		    const float4 c = tw[i];
@@ -451,12 +457,12 @@ __device__ __forceinline__ float frame_analyze_fast(const Ring rg, unsigned cand
 
 template <int G, int W, int L>
 __device__ __noinline__ float find_frame_fast(const Ring rg, unsigned pos_off,
-	const fsk_b200_geom &geo, int sel, const float4 *__restrict__ tw,
+	const fsk_b200_geom &geo, int sel, unsigned tw_s,
 	unsigned g, unsigned gmask, unsigned try_first, unsigned try_max, unsigned try_step,
 	float limit, unsigned long long &best_bits, float &best_a, unsigned &best_t)
 {
     return search_frames([&](unsigned t, unsigned long long &bits, float &a) {
-	return frame_analyze_fast<G, W, L>(rg, ring_wrap(pos_off + t, rg.R), geo, sel, tw,
+	return frame_analyze_fast<G, W, L>(rg, ring_wrap(pos_off + t, rg.R), geo, sel, tw_s,
 		g, gmask, bits, a);
     }, try_first, try_max, try_step, limit, best_bits, best_a, best_t);
 }
@@ -506,7 +512,7 @@ __device__ __forceinline__ void ring_issue(const Ring rg, const float *__restric
     unsigned off = (unsigned)off0;
     if (off >= rg.R)
 	off -= rg.R;
-    const unsigned ring_s = (unsigned)__cvta_generic_to_shared(rg.ring);
+    const unsigned ring_s = rg.ring_s;
     if (to <= n) {
 	/* whole range valid: at most two linear runs plus their mirrored heads */
 	const unsigned len = to - from;
@@ -635,7 +641,7 @@ __device__ __forceinline__ void ring_issue_bulk(const Ring rg, const float *__re
 	unsigned pos, unsigned pos_off, unsigned from, unsigned to, unsigned bar)
 {
     const unsigned len = to > from ? to - from : 0u;
-    const unsigned ring_s = smem_u32(rg.ring);
+    const unsigned ring_s = rg.ring_s;
     int off0 = (int)pos_off + (int)(from - pos);
     if (off0 < 0)
 	off0 += (int)rg.R;
@@ -670,9 +676,10 @@ __device__ __forceinline__ void ring_zero(const Ring rg, unsigned pos, unsigned 
 	unsigned off = (unsigned)off0;
 	if (off >= rg.R)
 	    off -= rg.R;
-	rg.ring[off] = 0.f;
+	float *ring = static_cast<float *>(__cvta_shared_to_generic(rg.ring_s));
+	ring[off] = 0.f;
 	if (off < rg.pad)
-	    rg.ring[rg.R + off] = 0.f;
+	    ring[rg.R + off] = 0.f;
     }
 }
 

@@ -119,7 +119,8 @@ k_find_frame(const __grid_constant__ fsk_b200_geom geo, const float4 *__restrict
     extern __shared__ float4 smem4[];
     const Smem sm = carve<G>(smem4, geo, tw_global, tw_in_smem, ring_floats);
     GROUP_VARS;
-    const Ring rg = { sm.ring, ring_floats, (geo.bit_nsamples + 3u) & ~3u };
+    const Ring rg = { smem_u32(sm.ring), ring_floats, (geo.bit_nsamples + 3u) & ~3u };
+    const unsigned tw_s = tw_in_smem ? smem_u32(sm.tw) : 0u;	/* the fast path requires the table in shared memory */
 
     for (unsigned s = (blockIdx.x * wpb + warp) * spw + sidx; s < a.nstreams;
 	    s += gridDim.x * wpb * spw) {
@@ -143,7 +144,7 @@ k_find_frame(const __grid_constant__ fsk_b200_geom geo, const float4 *__restrict
 		cp_async_commit();
 		cp_async_wait<0>();
 		__syncwarp(gmask);
-		conf = find_frame_fast<G, W, L>(rg, off & 3u, geo, sel, sm.tw, g, gmask,
+		conf = find_frame_fast<G, W, L>(rg, off & 3u, geo, sel, tw_s, g, gmask,
 			a.try_first[s], tmax, tstep, a.limit[s], bits, ampl, start);
 	    } else {
 		const GlobalSrc src = { x, n };
@@ -174,7 +175,8 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
     extern __shared__ float4 smem4[];
     const Smem sm = carve<G>(smem4, geo, tw_global, tw_in_smem, ring_floats);
     GROUP_VARS;
-    const Ring rg = { sm.ring, ring_floats, (geo.bit_nsamples + 3u) & ~3u };
+    const Ring rg = { smem_u32(sm.ring), ring_floats, (geo.bit_nsamples + 3u) & ~3u };
+    const unsigned tw_s = tw_in_smem ? smem_u32(sm.tw) : 0u;	/* the fast path requires the table in shared memory */
     const unsigned R = ring_floats;
 
     for (unsigned s = (blockIdx.x * wpb + warp) * spw + sidx; s < a.nstreams;
@@ -205,7 +207,7 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
 	unsigned kphase = 0;				/* bulk fill: number of barrier phases armed */
 	bool tail_fix = false;				/* bulk fill: [n, n4) holds row padding, not zeros */
 
-	const unsigned ring_s = smem_u32(rg.ring);
+	const unsigned ring_s = rg.ring_s;
 	unsigned foff = 0;				/* block fill: ring offset of `filled` */
 	/* request the ring content up to absolute index `to` (rounded up to whole blocks) */
 	auto request = [&](unsigned to) {
@@ -318,7 +320,7 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
 	    float amplitude, confidence;
 	    unsigned frame_start;
 	    if (MODE == 0)
-		confidence = find_frame_fast<G, W, L>(rg, pos_off, geo, sel, sm.tw, g, gmask,
+		confidence = find_frame_fast<G, W, L>(rg, pos_off, geo, sel, tw_s, g, gmask,
 			try_first, try_max, try_step, lc.confidence_search_limit,
 			bits, amplitude, frame_start);		/* :1265 */
 	    else
@@ -372,7 +374,7 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
 		    unsigned frame_start2;
 		    /* `carrier` is 1 by now, so the data string is searched (:1378) */
 		    if (MODE == 0)
-			confidence2 = find_frame_fast<G, W, L>(rg, pos_off, geo, 0, sm.tw, g,
+			confidence2 = find_frame_fast<G, W, L>(rg, pos_off, geo, 0, tw_s, g,
 				gmask, try_first, try_max, try_step, INFINITY,
 				bits2, amplitude2, frame_start2);
 		    else
@@ -777,7 +779,7 @@ static int pick_shape(const CudaEngine *ce, const fsk_b200_geom *g, unsigned nee
 	G <<= 1;
 	fast = split_for(G, g->n_bits, ce->split, &W, &L);
     }
-    if (g->bit_nsamples > FAST_MAX_N * (unsigned)L)
+    if (g->bit_nsamples > FAST_MAX_N * (unsigned)L || !sh->tw_in_smem)
 	fast = false;
 
     int wpb = ce->wpb ? ce->wpb : 2;
@@ -791,7 +793,7 @@ static int pick_shape(const CudaEngine *ce, const fsk_b200_geom *g, unsigned nee
 	if (wpb > 1) { wpb--; continue; }
 	if (G < 32) {
 	    G <<= 1;
-	    fast = split_for(G, g->n_bits, ce->split, &W, &L) && g->bit_nsamples <= FAST_MAX_N * (unsigned)L;
+	    fast = split_for(G, g->n_bits, ce->split, &W, &L) && g->bit_nsamples <= FAST_MAX_N * (unsigned)L && sh->tw_in_smem;
 	    continue;
 	}
 	if (ring) { ring = 0; fast = false; continue; }	/* not even one ring fits: read global memory */
