@@ -230,11 +230,18 @@ def run_ours(a):
     tcfg = mm.tx_config_from(cfg)
     spb = float(params.nsamples_per_bit)
     frame = params.frame_nsamples
-    nwords = max(1, (n - int(4 * spb) - int(spb)) // frame)
+    # transmitter frame length (src/minimodem.c:131-132, :96-111: size_t * float truncations)
+    bit = int(np.float32(np.float32(int(cfg.sample_rate)) / np.float32(cfg.data_rate)) + np.float32(0.5))
+    tx_frame = (int(np.float32(bit) * np.float32(tcfg.nstartbits)) if tcfg.nstartbits > 0 else 0) \
+        + params.n_data_bits * bit + (int(np.float32(bit) * np.float32(tcfg.nstopbits)) if tcfg.nstopbits > 0 else 0)
+    max_lead = 0 if cfg.do_rx_sync else max(1, int(spb))   # no lead-in for sync modes (see tests)
+    overhead = (tcfg.leader_bits + tcfg.trailer_bits) * bit + tcfg.do_tx_sync_bytes * tx_frame + max_lead
+    nwords = max(1, (n - overhead) // tx_frame)
     gen = torch.Generator(device="cpu").manual_seed(20260922 + rank)
     mask = (1 << params.n_data_bits) - 1
     words = (torch.randint(32, 127, (S, nwords), generator=gen, dtype=torch.int32) & mask).to(dev)
-    lead = torch.randint(0, max(1, int(spb)), (S,), generator=gen, dtype=torch.int32).to(dev)
+    lead = (torch.randint(0, max_lead, (S,), generator=gen, dtype=torch.int32) if max_lead
+            else torch.zeros(S, dtype=torch.int32)).to(dev)
     x = torch.empty((S, stride), dtype=torch.float32, device=dev)
     mm.tx_batch(tcfg, words, n, lead_in=lead, out=x, stride=stride)
     torch.cuda.synchronize()
@@ -292,6 +299,8 @@ def run_ours(a):
         recs = fr[s, :nfr[s]]
         recs = recs[recs["frame_start"] != mm.FRAME_REPORT]
         data = ((recs["bits_lo"].astype(np.int64)) >> shift) & mask
+        if cfg.do_rx_sync:
+            data = data[data != (cfg.sync_byte & mask)]          # the rx drops sync bytes (:1436-1439)
         got, want = data.tolist(), (w[s] & mask).tolist()
         assert any(got[i:i + len(want)] == want for i in range(len(got) - len(want) + 1)), "decode mismatch"
 
