@@ -87,24 +87,36 @@ def cpu_streams_on_host(a, nstreams):
     return m, x, nwords
 
 
-def cpu_measure(a, x, mode, steps=1, warmup=0):
+def cpu_measure(a, x, mode, steps=1, warmup=0, kinds=None):
+    """Times the CPU arm on `x`.  The thread count is chosen by measurement (all logical
+    CPUs, half, a quarter): on the 2-socket hosts of this pool the FFT-based reference
+    stops scaling well before all 128 hyper-threads are busy, and the best of the three
+    is reported with the thread count that achieved it."""
     import orc
     cores = len(os.sched_getaffinity(0))
     kind = "reference" if orc.have_ref() else "port"
-    best = []
-    for i in range(warmup + steps):
-        t = time.perf_counter()
-        total, fps, _ = orc.rx_many(mode, x, nsamples=a.nsamples, nthreads=cores, kind=kind)
-        dt = time.perf_counter() - t
-        if i >= warmup:
-            best.append(dt)
-    dt = sum(best) / len(best)
-    return dict(value=x.shape[0] * a.nsamples / dt / 1e6, unit="Msamples/s", cores=cores, kind=kind,
-                sample="%d streams x %d samples, %d threads, %s" % (
-                    x.shape[0], a.nsamples, cores,
-                    "unmodified src/fsk.c (oracle/_ref, FFT stand-in, not FFTW) behind the oracle rx loop"
-                    if kind == "reference" else "oracle port (two-bin direct DFT)"),
-                frames=int(total)), dt
+    out = {}
+    for k in (kinds or [kind]):
+        best = None
+        for nt in sorted({cores, max(1, cores // 2), max(1, cores // 4)}, reverse=True):
+            ts = []
+            for i in range(warmup + steps):
+                t = time.perf_counter()
+                total, fps, _ = orc.rx_many(mode, x, nsamples=a.nsamples, nthreads=nt, kind=k)
+                dt = time.perf_counter() - t
+                if i >= warmup:
+                    ts.append(dt)
+            dt = sum(ts) / len(ts)
+            if best is None or dt < best[0]:
+                best = (dt, nt, int(total))
+        dt, nt, total = best
+        out[k] = dict(value=x.shape[0] * a.nsamples / dt / 1e6, unit="Msamples/s", cores=nt, kind=k,
+                      sample="%d streams x %d samples, best of {%d, %d, %d} threads = %d, %s" % (
+                          x.shape[0], a.nsamples, cores, max(1, cores // 2), max(1, cores // 4), nt,
+                          "unmodified src/fsk.c (oracle/_ref; FFT stand-in, not FFTW) behind the oracle rx loop"
+                          if k == "reference" else "oracle port (two-bin direct DFT, no FFT): best-case CPU"),
+                      frames=total, seconds_per_pass=dt)
+    return out[kind], out[kind]["seconds_per_pass"], out
 
 
 def run_reference(a):
@@ -115,7 +127,7 @@ def run_reference(a):
     cores = len(os.sched_getaffinity(0))
     n = a.cpu_streams or max(16, min(2048, 16 * cores))
     mode, x, _ = cpu_streams_on_host(a, n)
-    cb, dt = cpu_measure(a, x, mode, steps=a.steps, warmup=a.warmup)
+    cb, dt, _ = cpu_measure(a, x, mode, steps=a.steps, warmup=a.warmup)
     line = {
         "impl": "reference", "metric": "audio Msamples/s demodulated (batched streams)",
         "value": cb["value"], "unit": "Msamples/s", "n_gpus": a.gpus, "steps": a.steps,
@@ -357,6 +369,7 @@ def run_ours(a):
 
     # ---- the reference CPU path on this box's host cores (rank 0, N=1 only)
     cpu = None
+    cpu_best = None
     if rank == 0 and world == 1 and not a.no_cpu:
         try:
             import orc
@@ -364,7 +377,9 @@ def run_ours(a):
             ncpu = a.cpu_streams or max(16, min(2048, 16 * cores))
             ncpu = min(ncpu, S)
             hostx = x[:ncpu, :n].cpu().numpy()
-            cpu, _ = cpu_measure(a, np.ascontiguousarray(hostx), orc.Mode(a.mode, sample_rate=a.rate), steps=2, warmup=1)
+            cpu, _, both = cpu_measure(a, np.ascontiguousarray(hostx), orc.Mode(a.mode, sample_rate=a.rate),
+                                       steps=1, warmup=1, kinds=["reference", "port"] if orc.have_ref() else ["port"])
+            cpu_best = both.get("port")
         except Exception as ex:  # the checker is optional for the number, never for the tests
             cpu = {"value": None, "unit": "Msamples/s", "cores": None, "kind": "unavailable", "sample": repr(ex)}
 
@@ -378,7 +393,8 @@ def run_ours(a):
                        "streams_per_gpu": S, "nsamples": n, "frame_nsamples": frame,
                        "l2": "inputs (%.1f GB per GPU) far exceed the 126 MB L2; no flush needed" % (S * stride * 4 / 1e9),
                        "parallelism": "streams sharded over %d GPU(s); NCCL broadcast of the plan only" % world},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu, "cpu_best_case": cpu_best, "e2e": e2e,
+            "gpu_launches": int(launches),
             "clocks": clocks, "lib": mm.version(),
         }
         print(json.dumps(line))
