@@ -412,3 +412,83 @@ def test_bell103_noise_sweep_confidence_match(kind):
             assert [orc.databits(m, f[0]) for f in got] == [orc.databits(m, f[0]) for f in want["frames"]]
     assert n_frames > 64 * 20
     assert n_flip <= 1
+
+
+# --------------------------------------------------------------------------
+# edge cases: empty / short / ragged streams, silence, noise only, output overflow + resume
+# --------------------------------------------------------------------------
+def test_rx_batch_edge_cases_ragged_batch():
+    m = orc.Mode("1200")
+    eng, cfg = engine_for(("1200", {}))
+    rng = np.random.default_rng(8)
+    base = orc.tx_words(m, rng.integers(32, 127, 30, dtype=np.uint32), 1.0, 4096, True)
+    d = m.derived()
+    streams = [
+        np.zeros(0, np.float32),                              # empty
+        base[:d.expect_nsamples - 1].copy(),                  # one sample short of a search window (:1229)
+        base[:d.expect_nsamples].copy(),                      # exactly one window
+        np.zeros(5000, np.float32),                           # silence: never any carrier
+        (0.3 * rng.standard_normal(20000)).astype(np.float32),   # noise only
+        base.copy(),                                          # a normal stream
+        base[:base.size // 2 + 7].copy(),                     # cut in the middle of a frame
+        np.concatenate([base, np.zeros(3000, np.float32), base]).astype(np.float32),   # carrier drop + re-acquire
+        (base * np.float32(1e-6)).astype(np.float32),         # tiny amplitude: confidence is scale free
+    ]
+    for lanes in (0, 16):
+        recs, st = rx_on_gpu(eng, streams, lanes=lanes)
+        for s, x in enumerate(streams):
+            want = orc.rx_run(m, x, literal=False)
+            compare_frames(as_oracle_frames(recs[s]), want["frames"], "edge stream %d (G=%d)" % (s, lanes))
+            compare_reports(reports_of(recs[s], st[s]), want["reports"], "edge stream %d (G=%d)" % (s, lanes))
+    assert len(recs[0]) == 0 and len(recs[1]) == 0 and len(recs[3]) == 0
+    assert sum(1 for r in recs[7] if int(r["frame_start"]) == mm.FRAME_REPORT) == 1
+
+
+def test_rx_batch_output_overflow_and_resume():
+    """A stream that fills its record buffer stops with done=0 and can be continued from its
+    saved state; the concatenated records equal those of an unbounded run."""
+    m = orc.Mode("1200")
+    eng, cfg = engine_for(("1200", {}))
+    rng = np.random.default_rng(9)
+    xs = [orc.tx_words(m, rng.integers(32, 127, 40, dtype=np.uint32), 1.0, 4096, True) for _ in range(5)]
+    n = max(len(a) for a in xs)
+    buf = np.zeros((len(xs), pad4(n)), np.float32)
+    for i, a in enumerate(xs):
+        buf[i, :len(a)] = a
+    d = torch.from_numpy(buf).to(dev())
+    lens = torch.from_numpy(np.array([len(a) for a in xs], np.int32)).to(dev())
+    full, st_full = eng.rx_batch(d, nsamples=n, nsamples_each=lens)
+    small, st = eng.rx_batch(d, nsamples=n, nsamples_each=lens, max_frames=10)
+    torch.cuda.synchronize()
+    s1 = mm.states_to_numpy(st)
+    assert (s1["done"] == 0).all() and (s1["nframes"] == 10).all()
+    big = torch.zeros_like(full)
+    _, st2 = eng.rx_batch(d, nsamples=n, nsamples_each=lens, max_frames=full.shape[1], frames=big, states=st)
+    torch.cuda.synchronize()
+    f_full, f_small, f_big = (mm.frames_to_numpy(t) for t in (full, small, big))
+    sf, s2 = mm.states_to_numpy(st_full), mm.states_to_numpy(st2)
+    assert (s2["done"] == 1).all() and np.array_equal(s2["nframes"], sf["nframes"])
+    for i in range(len(xs)):
+        k = int(sf["nframes"][i])
+        joined = np.concatenate([f_small[i, :10], f_big[i, 10:k]])
+        assert np.array_equal(joined, f_full[i, :k]), i
+    for key in ("pos", "carrier", "carrier_nsamples", "nframes_decoded", "confidence_total", "amplitude_total"):
+        assert np.array_equal(s2[key], sf[key]), key
+
+
+def test_find_frame_batch_degenerate_arguments():
+    eng, cfg = engine_for(("1200", {}))
+    p = eng.params
+    nstreams = 7                                              # not a multiple of anything
+    w = pad4(p.try_max_nocarrier + p.span_nsamples + 8)
+    x = torch.zeros((nstreams, w), dtype=torch.float32, device=dev())
+    i32 = lambda v: torch.full((nstreams,), v, dtype=torch.int32, device=dev())
+    tmax = i32(p.try_max_nocarrier)
+    tmax[0] = 0                                               # empty search range: loop never runs (:481)
+    nv = i32(w)
+    nv[1] = 0                                                 # no valid samples at all
+    fr = eng.find_frame_batch(x, nv, i32(0), tmax, i32(0), torch.full((nstreams,), 2.3, device=dev()))
+    torch.cuda.synchronize()
+    f = mm.frames_to_numpy(fr)
+    # silence: every bit ties (mag_mark == mag_space == 0 -> space), the start bit pattern mismatches
+    assert (f["confidence"] == 0).all() and (f["bits_lo"] == 0).all() and (f["frame_start"] == 0).all()
