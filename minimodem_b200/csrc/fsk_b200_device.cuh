@@ -378,7 +378,7 @@ __device__ __forceinline__ float frame_analyze_fast(const Ring rg, unsigned cand
 #pragma unroll
     for (int j = 0; j < W; j++) {
 	const unsigned w = j * WPP + wslot;
-	own[j] = w < nb && part == 0;
+	own[j] = w < nb && part == (unsigned)(j % L);	/* after the butterfly every lane of the window has the sums */
 	sig[j] = 0.f;
 	one[j] = false;
 	if (own[j]) {
@@ -405,7 +405,6 @@ __device__ __forceinline__ float frame_analyze_fast(const Ring rg, unsigned cand
 	    const float noise = one[j] ? mag_space : mag_mark;
 	    const unsigned e = geo.expect[sel][w];
 	    mismatch |= e != 2u && e != (one[j] ? 1u : 0u);	/* pass 1, :211 */
-	    ts += sig[j];
 	    if (noise > FSK_FLT_EPSILON)			/* :279 */
 		tn += noise;
 	    if (one[j]) {
@@ -422,14 +421,22 @@ __device__ __forceinline__ float frame_analyze_fast(const Ring rg, unsigned cand
 	ampl_out = 0.f;
 	return 0.f;
     }
-    ts = group_sum<G>(ts, gmask);
+    /* total_sig = sum over marks + sum over spaces; the mark count rides above the bits when
+     * the frame is short enough (disjoint bit positions: OR == ADD) */
     tn = group_sum<G>(tn, gmask);
     am = group_sum<G>(am, gmask);
     as = group_sum<G>(as, gmask);
-    nm = group_add<G>(nm, gmask);
-    blo = group_or<G>(blo, gmask);
-    if (nb > 32u)
-	bhi = group_or<G>(bhi, gmask);
+    ts = am + as;
+    if (nb <= 24u) {
+	const unsigned packed = group_add<G>(blo | (nm << 24), gmask);
+	blo = packed & 0xffffffu;
+	nm = packed >> 24;
+    } else {
+	nm = group_add<G>(nm, gmask);
+	blo = group_or<G>(blo, gmask);
+	if (nb > 32u)
+	    bhi = group_or<G>(bhi, gmask);
+    }
 
     const unsigned n_space = nb - nm;
     const float snr = fast_div(ts, tn);					/* :292, may be +inf */
