@@ -236,6 +236,27 @@ int fsk_b200_rx_batch_host(fsk_b200_engine *e, const float *host_samples, size_t
 	fsk_b200_frame *host_frames, uint32_t max_frames,
 	fsk_b200_stream_state *host_states);
 
+/* N2 -- 16-bit PCM ingest (the reference transmitter's default sample format, read back by
+ * its rx as float = short / 32768: src/simpleaudio-sndfile.c:43-57, src/minimodem.c:786-788).
+ * fsk_b200_s16_to_f32: device conversion (exact: a power-of-two scale), asynchronous on `stream`.
+ * fsk_b200_rx_batch_host_s16: like fsk_b200_rx_batch_host, but the host streams are int16 --
+ * half the bytes cross PCIe, the widening happens on the device. */
+int fsk_b200_s16_to_f32(const int16_t *src, float *dst, size_t nstreams, size_t stride, void *stream);
+int fsk_b200_rx_batch_host_s16(fsk_b200_engine *e, const int16_t *host_samples, size_t nstreams,
+	size_t stride, uint32_t nsamples_all,
+	fsk_b200_frame *host_frames, uint32_t max_frames,
+	fsk_b200_stream_state *host_states);
+
+/* N1 -- on-device databits decode for the stateless ASCII decoder
+ * (databits_decode_ascii8, src/databits_ascii.c:35-44, applied as the rx loop does at
+ * src/minimodem.c:1415-1446: prev-stop chop, bit_window, optional bit_reverse, sync-byte
+ * suppression).  For every stream, the records [0, states[s].nframes) of
+ * frames[s*max_frames ...] become bytes in out[s*out_stride ...]; out_count[s] receives the
+ * number of bytes (at most out_stride).  All pointers are device memory. */
+int fsk_b200_decode_ascii_batch(const fsk_b200_rx_params *p, const fsk_b200_frame *frames,
+	const fsk_b200_stream_state *states, size_t nstreams, uint32_t max_frames,
+	uint8_t *out, uint32_t out_stride, uint32_t *out_count, void *stream);
+
 /* Upper bound on frame records a stream of nsamples can produce. */
 uint32_t fsk_b200_max_frames(const fsk_b200_rx_params *p, uint32_t nsamples);
 

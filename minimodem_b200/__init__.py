@@ -10,6 +10,6 @@ raises otherwise.
 from .api import (  # noqa: F401
     LIB_PATH, Frame, RxConfig, RxParams, RxEngine, FskPlan, StreamState, TxConfig,
     build, lib, rx_config_for_mode, rx_params, frame_databits, max_frames, tx_batch,
-    version, launch_count, sin_table, frames_to_numpy, states_to_numpy, tx_config_from,
+    version, launch_count, sin_table, frames_to_numpy, states_to_numpy, tx_config_from, s16_to_f32,
     FRAME_DTYPE, STATE_DTYPE, STATE_WORDS, FRAME_ACQUIRED, FRAME_REPORT, EXPORTS,
 )

@@ -99,6 +99,7 @@ EXPORTS = [
     "fsk_b200_engine_destroy", "fsk_b200_engine_params", "fsk_b200_engine_tune",
     "fsk_b200_find_frame_batch", "fsk_b200_rx_batch", "fsk_b200_rx_batch_host",
     "fsk_b200_max_frames", "fsk_b200_frame_databits", "fsk_b200_tx_batch", "fsk_b200_sin_table",
+    "fsk_b200_s16_to_f32", "fsk_b200_rx_batch_host_s16", "fsk_b200_decode_ascii_batch",
     "fsk_b200_version", "fsk_b200_launch_count", "fsk_b200_last_error",
 ]
 
@@ -163,6 +164,14 @@ def lib():
     L.fsk_b200_tx_batch.argtypes = [C.POINTER(TxConfig), C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32,
                                     C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_uint32, C.c_void_p]
     L.fsk_b200_tx_batch.restype = C.c_int
+    L.fsk_b200_s16_to_f32.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]
+    L.fsk_b200_s16_to_f32.restype = C.c_int
+    L.fsk_b200_rx_batch_host_s16.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_uint32,
+                                             C.c_void_p, C.c_uint32, C.c_void_p]
+    L.fsk_b200_rx_batch_host_s16.restype = C.c_int
+    L.fsk_b200_decode_ascii_batch.argtypes = [C.POINTER(RxParams), C.c_void_p, C.c_void_p, C.c_size_t,
+                                              C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    L.fsk_b200_decode_ascii_batch.restype = C.c_int
     L.fsk_b200_sin_table.argtypes = [C.POINTER(C.c_float), C.c_uint, C.c_float]
     L.fsk_b200_sin_table.restype = None
     L.fsk_b200_version.restype = C.c_char_p
@@ -373,6 +382,40 @@ class RxEngine:
             _err("fsk_b200_rx_batch_host", rc)
         return frames_out, states_out
 
+    def rx_batch_host_s16(self, samples, nsamples=None, max_frames=None, frames_out=None, states_out=None):
+        """rx_batch_host for int16 PCM host streams ([nstreams, stride] int16 numpy array or pinned
+        CPU torch tensor): half the PCIe bytes, widened to float (x/32768) on the device."""
+        def hptr(t):
+            return C.c_void_p(t.data_ptr()) if hasattr(t, "data_ptr") else t.ctypes.data_as(C.c_void_p)
+        nstreams, stride = samples.shape
+        n_all = int(nsamples if nsamples is not None else stride)
+        if max_frames is None:
+            max_frames = self.max_frames(n_all)
+        if frames_out is None:
+            frames_out = np.zeros((nstreams, max_frames), FRAME_DTYPE)
+        if states_out is None:
+            states_out = np.zeros(nstreams, STATE_DTYPE)
+        rc = lib().fsk_b200_rx_batch_host_s16(self._e, hptr(samples), nstreams, stride, n_all,
+                                              hptr(frames_out), max_frames, hptr(states_out))
+        if rc:
+            _err("fsk_b200_rx_batch_host_s16", rc)
+        return frames_out, states_out
+
+    def decode_ascii_batch(self, frames, states, out_stride=None, stream=None):
+        """Device-side databits_decode_ascii8 over the records of rx_batch (CUDA tensors in,
+        (bytes [nstreams, out_stride] uint8, counts [nstreams] int32) CUDA tensors out)."""
+        torch = _torch()
+        nstreams, max_frames = frames.shape[0], frames.shape[1]
+        out_stride = int(out_stride or max_frames)
+        out = torch.zeros((nstreams, out_stride), dtype=torch.uint8, device=frames.device)
+        cnt = torch.zeros((nstreams,), dtype=torch.int32, device=frames.device)
+        rc = lib().fsk_b200_decode_ascii_batch(C.byref(self.params), _ptr(frames), _ptr(states), nstreams,
+                                               max_frames, _ptr(out), out_stride, _ptr(cnt),
+                                               _stream_handle(stream))
+        if rc:
+            _err("fsk_b200_decode_ascii_batch", rc)
+        return out, cnt
+
     def destroy(self):
         if self._e:
             lib().fsk_b200_engine_destroy(self._e)
@@ -413,6 +456,18 @@ def tx_batch(cfg, words, nsamples_out, lead_in=None, table=None, out=None, strid
                                  _stream_handle(stream))
     if rc:
         _err("fsk_b200_tx_batch", rc)
+    return out
+
+
+def s16_to_f32(src, out=None, stream=None):
+    """[nstreams, stride] int16 CUDA tensor -> float32 (x/32768) on the device."""
+    torch = _torch()
+    nstreams, stride = src.shape
+    if out is None:
+        out = torch.empty((nstreams, stride), dtype=torch.float32, device=src.device)
+    rc = lib().fsk_b200_s16_to_f32(_ptr(src), _ptr(out), nstreams, stride, _stream_handle(stream))
+    if rc:
+        _err("fsk_b200_s16_to_f32", rc)
     return out
 
 

@@ -456,6 +456,43 @@ int fsk_b200_rx_batch_host(fsk_b200_engine *e, const float *host_samples, size_t
 	    stride, nsamples_all, host_frames, max_frames, host_states);
 }
 
+int fsk_b200_s16_to_f32(const int16_t *src, float *dst, size_t nstreams, size_t stride, void *stream)
+{
+    if (!src || !dst || (stride & 3) || ((uintptr_t)dst & 15) || ((uintptr_t)src & 7)) {
+	fsk_b200_set_error("s16_to_f32: stride must be a multiple of 4, src 8-byte and dst 16-byte aligned");
+	return -EINVAL;
+    }
+    return fsk_b200_cuda_s16_to_f32(src, dst, nstreams, stride, stream);
+}
+
+int fsk_b200_rx_batch_host_s16(fsk_b200_engine *e, const int16_t *host_samples, size_t nstreams,
+	size_t stride, uint32_t nsamples_all, fsk_b200_frame *host_frames, uint32_t max_frames,
+	fsk_b200_stream_state *host_states)
+{
+    if (nstreams == 0)
+	return 0;
+    if (!host_samples || !host_frames || !host_states || (stride & 3) || max_frames == 0) {
+	fsk_b200_set_error("rx_batch_host_s16: bad argument (stride must be a multiple of 4)");
+	return -EINVAL;
+    }
+    return fsk_b200_cuda_rx_batch_host_s16(e->ce, &e->geom, &e->loopc, host_samples, nstreams,
+	    stride, nsamples_all, host_frames, max_frames, host_states);
+}
+
+int fsk_b200_decode_ascii_batch(const fsk_b200_rx_params *p, const fsk_b200_frame *frames,
+	const fsk_b200_stream_state *states, size_t nstreams, uint32_t max_frames,
+	uint8_t *out, uint32_t out_stride, uint32_t *out_count, void *stream)
+{
+    if (!p || !frames || !states || !out || !out_count || out_stride == 0 || max_frames == 0) {
+	fsk_b200_set_error("decode_ascii_batch: NULL argument");
+	return -EINVAL;
+    }
+    /* src/minimodem.c:1415 (drop the previous stop bit) + bit_window's offset */
+    unsigned shift = (p->nstopbits != 0.0f ? 1u : 0u) + (unsigned)p->nstartbits;
+    return fsk_b200_cuda_decode_ascii(shift, p->n_data_bits, p->msb_first, p->do_rx_sync, p->sync_byte,
+	    frames, states, nstreams, max_frames, out, out_stride, out_count, stream);
+}
+
 void fsk_b200_sin_table(float *out, unsigned int len, float mag)
 {
     for (unsigned int i = 0; i < len; i++)

@@ -530,6 +530,70 @@ __global__ void k_tx(const __grid_constant__ fsk_b200_tx_config c, TxLens L,
 	o[i] = 0.f;
 }
 
+/* ------------------------------------------------------------------------ */
+/* N2: int16 PCM -> float32 (x / 32768, exact), 8 samples per thread        */
+/* ------------------------------------------------------------------------ */
+__global__ void k_s16_to_f32(const int4 *__restrict__ src, float4 *__restrict__ dst, size_t n8)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n8)
+	return;
+    const int4 v = __ldg(src + i);
+    const float k = 1.0f / 32768.0f;
+    float4 a, b;
+    a.x = (float)(short)(v.x & 0xffff) * k;  a.y = (float)(short)(v.x >> 16) * k;
+    a.z = (float)(short)(v.y & 0xffff) * k;  a.w = (float)(short)(v.y >> 16) * k;
+    b.x = (float)(short)(v.z & 0xffff) * k;  b.y = (float)(short)(v.z >> 16) * k;
+    b.z = (float)(short)(v.w & 0xffff) * k;  b.w = (float)(short)(v.w >> 16) * k;
+    dst[2 * i] = a;
+    dst[2 * i + 1] = b;
+}
+
+/* generic tail / unaligned variant: one sample per thread */
+__global__ void k_s16_to_f32_scalar(const short *__restrict__ src, float *__restrict__ dst, size_t n)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+	dst[i] = (float)src[i] * (1.0f / 32768.0f);
+}
+
+/* ------------------------------------------------------------------------ */
+/* N1: frame records -> bytes, databits_decode_ascii8 (src/databits_ascii.c:35-44)
+ * behind the bit chop of src/minimodem.c:1415-1446; one thread per stream    */
+/* ------------------------------------------------------------------------ */
+__global__ void k_decode_ascii(unsigned shift, unsigned n_data_bits, int msb_first, int do_rx_sync,
+	unsigned long long sync_byte, const fsk_b200_frame *__restrict__ frames,
+	const fsk_b200_stream_state *__restrict__ states, unsigned nstreams, uint32_t max_frames,
+	uint8_t *__restrict__ out, uint32_t out_stride, uint32_t *__restrict__ out_count)
+{
+    const unsigned s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nstreams)
+	return;
+    const unsigned nrec = min(states[s].nframes, max_frames);
+    const uint32_t *rec = reinterpret_cast<const uint32_t *>(frames + (size_t)s * max_frames);
+    uint8_t *o = out + (size_t)s * out_stride;
+    unsigned k = 0;
+    const unsigned long long mask = n_data_bits < 64 ? (1ull << n_data_bits) - 1ull : ~0ull;
+    for (unsigned i = 0; i < nrec; i++, rec += 5) {
+	if (rec[4] == FSK_B200_FRAME_REPORT)
+	    continue;				/* a carrier-session report, not a frame */
+	unsigned long long bits = ((unsigned long long)rec[1] << 32) | rec[0];
+	bits = (bits >> shift) & mask;		/* :1415 chop + bit_window (src/databits.h:35-46) */
+	if (msb_first) {			/* bit_reverse keeps 32 bits (src/databits.h:21-33) */
+	    unsigned r = 0;
+	    for (unsigned b = 0; b < n_data_bits; b++)
+		r = (r << 1) | (unsigned)((bits >> b) & 1ull);
+	    bits = r;
+	}
+	if (do_rx_sync && bits == sync_byte)	/* :1436-1439 */
+	    continue;
+	if (k < out_stride)
+	    o[k] = (uint8_t)(bits & 0xff);	/* databits_decode_ascii8 */
+	k++;
+    }
+    out_count[s] = min(k, out_stride);
+}
+
 /* ======================================================================== */
 /* host side of the CUDA translation unit                                   */
 /* ======================================================================== */
@@ -554,6 +618,7 @@ struct CudaEngine {
     size_t d_mags_cap;
     /* host-batch slabs */
     float *d_slab[2];
+    int16_t *d_slab_s16[2];
     fsk_b200_frame *d_slab_frames[2];
     fsk_b200_stream_state *d_slab_states[2];
     size_t slab_streams, slab_stride, slab_max_frames;
@@ -606,6 +671,7 @@ extern "C" void fsk_b200_cuda_engine_destroy(void *p)
     cudaFree(ce->d_mags);
     for (int i = 0; i < 2; i++) {
 	cudaFree(ce->d_slab[i]);
+	cudaFree(ce->d_slab_s16[i]);
 	cudaFree(ce->d_slab_frames[i]);
 	cudaFree(ce->d_slab_states[i]);
 	if (ce->st[i])
@@ -939,13 +1005,13 @@ extern "C" int fsk_b200_cuda_rx_batch(void *p, const fsk_b200_geom *g, const fsk
     return 0;
 }
 
-/* host buffers in, host results out: slabs of streams, copy/compute overlap */
-extern "C" int fsk_b200_cuda_rx_batch_host(void *p, const fsk_b200_geom *g, const fsk_b200_loopc *lc,
-	const float *host_samples, size_t nstreams, size_t stride, uint32_t nsamples_all,
+/* host buffers in, host results out: slabs of streams, copy/compute overlap.
+ * elem = 4: float32 samples; elem = 2: int16 samples, widened on the device. */
+static int rx_batch_host_common(CudaEngine *ce, const fsk_b200_geom *g, const fsk_b200_loopc *lc,
+	const void *host_samples, int elem, size_t nstreams, size_t stride, uint32_t nsamples_all,
 	fsk_b200_frame *host_frames, uint32_t max_frames, fsk_b200_stream_state *host_states)
 {
-    CudaEngine *ce = (CudaEngine *)p;
-    /* slab = as many streams as fit ~256 MiB of samples */
+    /* slab = as many streams as fit ~256 MiB of float samples */
     size_t slab = ((size_t)256 << 20) / (stride * sizeof(float));
     if (slab < 1) slab = 1;
     if (slab > nstreams) slab = nstreams;
@@ -954,6 +1020,7 @@ extern "C" int fsk_b200_cuda_rx_batch_host(void *p, const fsk_b200_geom *g, cons
 	    cudaFree(ce->d_slab[i]); ce->d_slab[i] = NULL;
 	    cudaFree(ce->d_slab_frames[i]); ce->d_slab_frames[i] = NULL;
 	    cudaFree(ce->d_slab_states[i]); ce->d_slab_states[i] = NULL;
+	    cudaFree(ce->d_slab_s16[i]); ce->d_slab_s16[i] = NULL;
 	    CUDA_TRY(cudaMalloc(&ce->d_slab[i], slab * stride * sizeof(float)));
 	    CUDA_TRY(cudaMalloc(&ce->d_slab_frames[i], slab * (size_t)max_frames * sizeof(fsk_b200_frame)));
 	    CUDA_TRY(cudaMalloc(&ce->d_slab_states[i], slab * sizeof(fsk_b200_stream_state)));
@@ -964,12 +1031,24 @@ extern "C" int fsk_b200_cuda_rx_batch_host(void *p, const fsk_b200_geom *g, cons
 	ce->slab_stride = stride;
 	ce->slab_max_frames = max_frames;
     }
+    if (elem == 2)
+	for (int i = 0; i < 2; i++)
+	    if (!ce->d_slab_s16[i])
+		CUDA_TRY(cudaMalloc(&ce->d_slab_s16[i], ce->slab_streams * stride * sizeof(int16_t)));
     int k = 0;
     for (size_t s0 = 0; s0 < nstreams; s0 += slab, k ^= 1) {
 	const size_t ns = nstreams - s0 < slab ? nstreams - s0 : slab;
 	cudaStream_t st = ce->st[k];
-	CUDA_TRY(cudaMemcpyAsync(ce->d_slab[k], host_samples + s0 * stride, ns * stride * sizeof(float),
-		    cudaMemcpyHostToDevice, st));
+	if (elem == 4) {
+	    CUDA_TRY(cudaMemcpyAsync(ce->d_slab[k], (const float *)host_samples + s0 * stride,
+			ns * stride * sizeof(float), cudaMemcpyHostToDevice, st));
+	} else {
+	    CUDA_TRY(cudaMemcpyAsync(ce->d_slab_s16[k], (const int16_t *)host_samples + s0 * stride,
+			ns * stride * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+	    int rc = fsk_b200_cuda_s16_to_f32(ce->d_slab_s16[k], ce->d_slab[k], ns, stride, st);
+	    if (rc)
+		return rc;
+	}
 	CUDA_TRY(cudaMemcpyAsync(ce->d_slab_states[k], host_states + s0, ns * sizeof(fsk_b200_stream_state),
 		    cudaMemcpyHostToDevice, st));
 	int rc = fsk_b200_cuda_rx_batch(ce, g, lc, ce->d_slab[k], ns, stride, NULL, nsamples_all,
@@ -983,6 +1062,63 @@ extern "C" int fsk_b200_cuda_rx_batch_host(void *p, const fsk_b200_geom *g, cons
     }
     CUDA_TRY(cudaStreamSynchronize(ce->st[0]));
     CUDA_TRY(cudaStreamSynchronize(ce->st[1]));
+    return 0;
+}
+
+extern "C" int fsk_b200_cuda_rx_batch_host(void *p, const fsk_b200_geom *g, const fsk_b200_loopc *lc,
+	const float *host_samples, size_t nstreams, size_t stride, uint32_t nsamples_all,
+	fsk_b200_frame *host_frames, uint32_t max_frames, fsk_b200_stream_state *host_states)
+{
+    return rx_batch_host_common((CudaEngine *)p, g, lc, host_samples, 4, nstreams, stride, nsamples_all,
+	    host_frames, max_frames, host_states);
+}
+
+extern "C" int fsk_b200_cuda_rx_batch_host_s16(void *p, const fsk_b200_geom *g, const fsk_b200_loopc *lc,
+	const int16_t *host_samples, size_t nstreams, size_t stride, uint32_t nsamples_all,
+	fsk_b200_frame *host_frames, uint32_t max_frames, fsk_b200_stream_state *host_states)
+{
+    return rx_batch_host_common((CudaEngine *)p, g, lc, host_samples, 2, nstreams, stride, nsamples_all,
+	    host_frames, max_frames, host_states);
+}
+
+extern "C" int fsk_b200_cuda_s16_to_f32(const int16_t *src, float *dst, size_t nstreams, size_t stride,
+	void *stream)
+{
+    const size_t n = nstreams * stride;
+    if (n == 0)
+	return 0;
+    if ((n & 7) == 0 && ((uintptr_t)src & 15) == 0) {
+	const size_t n8 = n / 8;
+	k_s16_to_f32<<<(unsigned)((n8 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+		reinterpret_cast<const int4 *>(src), reinterpret_cast<float4 *>(dst), n8);
+    } else {
+	k_s16_to_f32_scalar<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, dst, n);
+    }
+    g_launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+	fsk_b200_set_error("s16_to_f32 launch: %s", cudaGetErrorString(e));
+	return -EIO;
+    }
+    return 0;
+}
+
+extern "C" int fsk_b200_cuda_decode_ascii(unsigned shift, unsigned n_data_bits, int msb_first,
+	int do_rx_sync, unsigned long long sync_byte, const fsk_b200_frame *frames,
+	const fsk_b200_stream_state *states, size_t nstreams, uint32_t max_frames, uint8_t *out,
+	uint32_t out_stride, uint32_t *out_count, void *stream)
+{
+    if (nstreams == 0)
+	return 0;
+    k_decode_ascii<<<(unsigned)((nstreams + 127) / 128), 128, 0, (cudaStream_t)stream>>>(shift,
+	    n_data_bits, msb_first, do_rx_sync, sync_byte, frames, states, (unsigned)nstreams,
+	    max_frames, out, out_stride, out_count);
+    g_launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+	fsk_b200_set_error("decode_ascii launch: %s", cudaGetErrorString(e));
+	return -EIO;
+    }
     return 0;
 }
 

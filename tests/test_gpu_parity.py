@@ -492,3 +492,44 @@ def test_find_frame_batch_degenerate_arguments():
     f = mm.frames_to_numpy(fr)
     # silence: every bit ties (mag_mark == mag_space == 0 -> space), the start bit pattern mismatches
     assert (f["confidence"] == 0).all() and (f["bits_lo"] == 0).all() and (f["frame_start"] == 0).all()
+
+
+# --------------------------------------------------------------------------
+# "next" rows: N2 16-bit PCM ingest, N1 on-device ASCII databits decode
+# --------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["01-self-test-1200", "02-self-test-300", "80-SAME", "81-ascii7", "60-multibyte"])
+def test_s16_ingest_and_device_ascii_decode(name):
+    """The reference transmitter's default format is S16; its rx reads short/32768
+    (src/simpleaudio-sndfile.c:43-57).  The int16 host path must give exactly the records of the
+    float path, and the device decoder exactly the bytes the reference printed."""
+    case = refcases.BY_NAME[name]
+    g = gu.load(name)
+    _, rx = gu.modes(case)
+    a = gu.audio(case, g)
+    s16 = np.round(a * 32768.0).astype(np.int16)
+    assert np.array_equal(s16.astype(np.float32) * np.float32(1 / 32768.0), a)     # vectors really are S16
+    eng, cfg = engine_for(case)
+    n = a.size
+    stride = pad4(n)
+    nstreams = 3
+    hs = np.zeros((nstreams, stride), np.int16)
+    hf = np.zeros((nstreams, stride), np.float32)
+    hs[:, :n] = s16
+    hf[:, :n] = a
+    fr_f, st_f = eng.rx_batch_host(hf, nsamples=n)
+    fr_s, st_s = eng.rx_batch_host_s16(hs, nsamples=n)
+    assert np.array_equal(st_f, st_s)
+    k = int(st_f["nframes"][0])
+    assert k > 0 and np.array_equal(fr_f[:, :k], fr_s[:, :k])
+    # device conversion kernel on its own
+    d = mm.s16_to_f32(torch.from_numpy(hs).to(dev()))
+    torch.cuda.synchronize()
+    assert np.array_equal(d.cpu().numpy(), hf)
+    # device decode of the device-resident records
+    frames, states = eng.rx_batch(d, nsamples=n)
+    out, cnt = eng.decode_ascii_batch(frames, states)
+    torch.cuda.synchronize()
+    o, c = out.cpu().numpy(), cnt.cpu().numpy()
+    want = bytes(g["stdout"])
+    for s in range(nstreams):
+        assert bytes(o[s, :c[s]]) == want, s
