@@ -311,11 +311,17 @@ __device__ __forceinline__ unsigned group_add(unsigned v, unsigned gmask)
  * to memory, and the frame statistics of src/fsk.c:271-336 are formed by
  * butterfly reductions over the group instead of a serial loop over the bits
  * (same terms, different but fixed summation order). */
-template <int G, int W, int L>
+template <int G, int W, int L, bool WS = false>
 __device__ __forceinline__ float frame_analyze_fast(const Ring rg, unsigned cand_off,
 	const fsk_b200_geom &geo, int sel, unsigned tw_s,
-	unsigned g, unsigned gmask, unsigned long long &bits_out, float &ampl_out)
+	unsigned g, unsigned gmask_in, unsigned long long &bits_out, float &ampl_out)
 {
+    /* WS ("warp-synchronous"): the caller guarantees that all 32 lanes are here together, so
+     * shuffles and votes use the constant full mask (the shuffle distances stay inside a
+     * group); with a run-time group mask the compiler has to guard every shuffle with a
+     * MATCH/VOTE sequence.  A rejected candidate is then zeroed at the end instead of
+     * returning early. */
+    const unsigned gmask = WS ? 0xffffffffu : gmask_in;
     /* ring and twiddles are handed over as shared-window addresses and turned back into
      * pointers here, so that the compiler keeps them in the shared address space (LDS with
      * 32-bit addresses and immediate offsets) even though this code is not inlined */
@@ -416,7 +422,10 @@ __device__ __forceinline__ float frame_analyze_fast(const Ring rg, unsigned cand
 	    }
 	}
     }
-    if (__any_sync(gmask, mismatch)) {		/* pass 1 reject, src/fsk.c:211-212 */
+    /* pass 1 reject, src/fsk.c:211-212 */
+    const bool rejected = WS ? (__ballot_sync(0xffffffffu, mismatch) & gmask_in) != 0u
+			     : __any_sync(gmask, mismatch) != 0;
+    if (!WS && rejected) {
 	bits_out = 0;
 	ampl_out = 0.f;
 	return 0.f;
@@ -457,9 +466,51 @@ __device__ __forceinline__ float frame_analyze_fast(const Ring rg, unsigned cand
     divergence *= 2.f;						/* :312-313 */
     divergence = fast_div(divergence, (float)(int)nb);
 
+    if (WS && rejected) {
+	bits_out = 0;
+	ampl_out = 0.f;
+	return 0.f;
+    }
     bits_out = ((unsigned long long)bhi << 32) | blo;
     ampl_out = avg_bit_sig;					/* :342 */
     return snr * (1.0f - divergence);				/* :336 */
+}
+
+/* The zig-zag search of src/fsk.c:477-502 run warp-synchronously: every lane of the warp
+ * takes every trip of the loop; a group whose search is over (or that has no stream, `on`
+ * false) rides along on candidate 0 and drops the result.  SIMT would spend those trips
+ * waiting anyway; in exchange all shuffles inside use the constant full mask. */
+template <int G, int W, int L>
+__device__ __noinline__ float find_frame_ws(const Ring rg, unsigned pos_off,
+	const fsk_b200_geom &geo, int sel, unsigned tw_s, unsigned g, unsigned gmask, bool on,
+	unsigned try_first, unsigned try_max, unsigned try_step, float limit,
+	unsigned long long &best_bits, float &best_a, unsigned &best_t)
+{
+    float best_c = 0.f;
+    best_t = 0;
+    best_a = 0.f;
+    best_bits = 0;
+    bool searching = on;
+    for (int j = 0; __any_sync(0xffffffffu, searching); j++) {
+	const int up = (j & 1) ? 1 : -1;
+	const int t = (int)try_first + up * ((j + 1) / 2) * (int)try_step;
+	if (t >= (int)try_max)
+	    searching = false;					/* :481 */
+	const bool eval = searching && t >= 0;			/* :483 */
+	unsigned long long bits;
+	float a;
+	const float c = frame_analyze_fast<G, W, L, true>(rg, eval ? ring_wrap(pos_off + (unsigned)t, rg.R) : 0u,
+		geo, sel, tw_s, g, gmask, bits, a);
+	if (eval && best_c < c) {				/* :492: NaN and negatives never win */
+	    best_t = (unsigned)t;
+	    best_c = c;
+	    best_a = a;
+	    best_bits = bits;
+	    if (best_c >= limit)
+		searching = false;				/* :499 first to reach the limit wins */
+	}
+    }
+    return best_c;
 }
 
 template <int G, int W, int L>

@@ -434,6 +434,221 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
     }
 }
 
+
+/* ------------------------------------------------------------------------ */
+/* K2, warp-synchronous form (FSK_B200_FILL=3; measured 4 % slower than the     */
+/* group-masked loop): the 32/G streams of a warp step through the loop together,*/
+/* which lets every shuffle and vote use the constant full mask                */
+/* ------------------------------------------------------------------------ */
+template <int G, int W, int L>
+__global__ void __launch_bounds__(128, FSK_MINBLOCKS)
+k_rx_ws(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200_loopc lc,
+	const float4 *__restrict__ tw_global, unsigned ring_floats, unsigned lookahead,
+	const __grid_constant__ RxArgs a)
+{
+    extern __shared__ float4 smem4[];
+    const Smem sm = carve<G>(smem4, geo, tw_global, 1u, ring_floats);
+    GROUP_VARS;
+    const Ring rg = { smem_u32(sm.ring), ring_floats, (geo.bit_nsamples + 3u) & ~3u };
+    const unsigned tw_s = smem_u32(sm.tw);
+    const unsigned R = ring_floats;
+    const unsigned FULL = 0xffffffffu;
+    const unsigned need_max = lc.try_max_nocarrier - 1u + geo.span;
+
+    for (unsigned s0 = (blockIdx.x * wpb + warp) * spw; s0 < a.nstreams; s0 += gridDim.x * wpb * spw) {
+	const unsigned s = s0 + sidx;
+	const bool have = s < a.nstreams;
+	fsk_b200_stream_state st;
+	if (have)
+	    st = a.states[s];
+	else
+	    memset(&st, 0, sizeof(st));
+	bool alive = have && !st.done;
+	const float *x = a.samples + (size_t)(have ? s : 0) * a.stride;
+	const unsigned n = have ? (a.nsamples ? a.nsamples[s] : a.nsamples_all) : 0u;
+	fsk_b200_frame *out = a.frames + (size_t)(have ? s : 0) * a.max_frames;
+
+	unsigned pos = (unsigned)st.pos;
+	unsigned nframes = st.nframes;
+	unsigned carrier = st.carrier, noconfidence = st.noconfidence;
+	float track_amplitude = st.track_amplitude, peak_confidence = st.peak_confidence;
+	unsigned long long carrier_nsamples = st.carrier_nsamples;
+	float confidence_total = st.confidence_total, amplitude_total = st.amplitude_total;
+	unsigned nframes_decoded = st.nframes_decoded;
+	unsigned done = st.done;
+
+	unsigned pos_off = pos & 3u;		/* ring offset of `pos` */
+	unsigned filled = pos & ~3u;		/* absolute index up to which copies were issued */
+	unsigned foff = 0;			/* ring offset of `filled` */
+	auto request = [&](unsigned to) {	/* whole blocks up to `to`, never past what the ring can hold */
+	    const unsigned cap = (pos & ~3u) + R;
+	    while (filled < to && filled + RING_BLOCK <= cap) {
+		if (filled + RING_BLOCK <= n)
+		    ring_block<G>(rg, rg.ring_s, foff, x + filled, g);
+		else
+		    ring_block_tail<G>(rg, rg.ring_s, foff, x, n, filled, g);
+		filled += RING_BLOCK;
+		foff += RING_BLOCK;
+		if (foff >= R)
+		    foff = 0;
+	    }
+	};
+	__syncwarp();
+	if (alive)
+	    request(min((pos + need_max + 3u) & ~3u, (pos & ~3u) + R));
+	cp_async_commit();
+
+	for (;;) {
+	    unsigned remaining = 0;
+	    if (alive) {
+		if (pos >= n) { done = 1; alive = false; }			/* :1176 */
+		else {
+		    remaining = n - pos;
+		    if (remaining < lc.expect_nsamples) { done = 1; alive = false; }	/* :1229 */
+		    else if (nframes >= a.max_frames) alive = false;		/* output full: resumable */
+		}
+	    }
+	    if (!__any_sync(FULL, alive))
+		break;
+
+	    unsigned try_max = carrier ? lc.try_max_carrier : lc.try_max_nocarrier;	/* :1236-1241 */
+	    unsigned try_step = try_max / 3u;			/* :1248-1251 */
+	    if (try_step == 0)
+		try_step = 1;
+	    const unsigned try_first = carrier ? lc.nsamples_overscan : 0u;	/* :1263 */
+	    const int sel = carrier ? 0 : 1;			/* :1270 data / sync string */
+
+	    /* prefetch what the next iteration can need, wait only for what this one needs */
+	    bool late = false;
+	    if (alive) {
+		const unsigned need_now = (pos + try_max - 1u + geo.span + 3u) & ~3u;
+		late = filled < need_now;
+		request(min((pos + lookahead + need_max + 3u) & ~3u, (pos & ~3u) + R));
+	    }
+	    cp_async_commit();
+	    if (__any_sync(FULL, late))
+		cp_async_wait<0>();
+	    else
+		cp_async_wait<1>();
+	    __syncwarp();
+
+	    unsigned long long bits;
+	    float amplitude;
+	    unsigned frame_start;
+	    float confidence = find_frame_ws<G, W, L>(rg, pos_off, geo, sel, tw_s, g, gmask, alive,
+		    try_first, try_max, try_step, lc.confidence_search_limit,
+		    bits, amplitude, frame_start);		/* :1265 */
+
+	    bool want_refine = false;
+	    if (confidence < peak_confidence * 0.75f) {		/* :1278-1282 */
+		want_refine = true;
+		if (alive)
+		    peak_confidence = 0.f;
+	    }
+	    if (amplitude < track_amplitude * 0.25f)		/* :1286 */
+		confidence = 0.f;
+	    const bool confident = alive && !(confidence <= lc.confidence_threshold);	/* :1292 */
+	    unsigned advance = try_max;				/* :1318 */
+	    unsigned acquired = 0;
+	    if (alive && !confident) {
+		if (++noconfidence > 20u) {			/* :1295 */
+		    if (carrier) {
+			/* report_no_carrier(), :1299-1302, as a record */
+			if (g == 0)
+			    store_frame(out + nframes, carrier_nsamples, confidence_total,
+				    amplitude_total, FSK_B200_FRAME_REPORT);
+			nframes++;
+			carrier = 0;				/* :1303-1308 */
+			carrier_nsamples = 0;
+			confidence_total = 0.f;
+			amplitude_total = 0.f;
+			nframes_decoded = 0;
+			track_amplitude = 0.f;
+		    }
+		}
+	    }
+	    if (confident) {
+		carrier_nsamples += lc.frame_nsamples;		/* :1324 */
+		if (carrier) {
+		    carrier_nsamples += frame_start;		/* :1329-1330: the COARSE start */
+		    carrier_nsamples -= lc.nsamples_overscan;
+		} else {					/* :1332-1355 */
+		    carrier = 1;
+		    acquired = FSK_B200_FRAME_ACQUIRED;
+		    want_refine = true;
+		}
+	    }
+	    /* :1357-1389: the fine search, for the groups that want it (the whole warp rides along) */
+	    const bool refine = confident && want_refine && confidence < INFINITY && try_step > 1u;
+	    if (__any_sync(FULL, refine)) {
+		unsigned fine_step = try_max / 8u;
+		if (fine_step == 0)
+		    fine_step = 1;
+		unsigned long long bits2;
+		float amplitude2;
+		unsigned frame_start2;
+		/* `carrier` is 1 by now, so the data string is searched (:1378) */
+		const float confidence2 = find_frame_ws<G, W, L>(rg, pos_off, geo, 0, tw_s, g, gmask, refine,
+			try_first, try_max, fine_step, INFINITY, bits2, amplitude2, frame_start2);
+		if (refine && confidence2 > confidence) {
+		    bits = bits2;
+		    amplitude = amplitude2;
+		    frame_start = frame_start2;
+		}
+	    }
+	    if (confident) {
+		track_amplitude = (track_amplitude + amplitude) / 2.f;	/* :1391 */
+		if (peak_confidence < confidence)
+		    peak_confidence = confidence;
+		confidence_total += confidence;			/* :1397-1400 */
+		amplitude_total += amplitude;
+		nframes_decoded++;
+		noconfidence = 0;
+		if (g == 0)
+		    store_frame(out + nframes, bits, confidence, amplitude, frame_start | acquired);
+		nframes++;
+		advance = frame_start + lc.frame_nsamples - lc.nsamples_overscan;	/* :1407 */
+	    }
+	    if (alive) {
+		if (advance > remaining) { done = 1; alive = false; }	/* :1151 */
+		else {
+		    pos += advance;
+		    pos_off = ring_wrap(pos_off + advance, R);	/* advance < R by construction */
+		}
+	    }
+	    /* a group that skipped past everything requested so far restarts its ring; the copies
+	     * still in flight into it have to land first */
+	    const bool rebase = alive && filled < (pos & ~3u);
+	    if (__any_sync(FULL, rebase)) {
+		cp_async_wait<0>();
+		if (rebase) {
+		    filled = pos & ~3u;
+		    pos_off = pos & 3u;
+		    foff = 0;
+		}
+	    }
+	    __syncwarp();		/* every read of this window precedes the next copies */
+	}
+	cp_async_wait<0>();		/* nothing in flight into these rings when the slots are reused */
+	__syncwarp();
+
+	if (have && g == 0) {
+	    st.pos = pos;
+	    st.nframes = nframes;
+	    st.carrier = carrier;
+	    st.noconfidence = noconfidence;
+	    st.track_amplitude = track_amplitude;
+	    st.peak_confidence = peak_confidence;
+	    st.carrier_nsamples = carrier_nsamples;
+	    st.confidence_total = confidence_total;
+	    st.amplitude_total = amplitude_total;
+	    st.nframes_decoded = nframes_decoded;
+	    st.done = done;
+	    a.states[s] = st;
+	}
+    }
+}
+
 /* ------------------------------------------------------------------------ */
 /* full-spectrum magnitudes for fsk_detect_carrier (src/fsk.c:543-581)      */
 /* ------------------------------------------------------------------------ */
@@ -654,8 +869,8 @@ extern "C" void *fsk_b200_cuda_engine_new(void)
     if ((e = getenv("FSK_B200_WPB"))) ce->wpb = atoi(e);
     if ((e = getenv("FSK_B200_RING"))) ce->ring = atoi(e);
     if ((e = getenv("FSK_B200_SPLIT"))) ce->split = atoi(e);
-    ce->fill = 0;		/* cp.async (LDGSTS) by all lanes; FSK_B200_FILL=1 selects TMA bulk copies */
-    if ((e = getenv("FSK_B200_FILL"))) ce->fill = atoi(e) ? 1 : 0;
+    ce->fill = 0;		/* see the dispatch in fsk_b200_cuda_rx_batch */
+    if ((e = getenv("FSK_B200_FILL"))) ce->fill = atoi(e);
     return ce;
 }
 
@@ -771,6 +986,10 @@ struct Shape {
     X(16, 1, 4) X(16, 2, 4) X(16, 3, 4) X(16, 4, 4) \
     X(32, 1, 1) X(32, 2, 1) X(32, 1, 2) X(32, 2, 2) X(32, 3, 2) X(32, 4, 2) X(32, 1, 4) X(32, 2, 4) X(32, 3, 4) X(32, 4, 4)
 #endif
+
+/* the alternative kernels (TMA bulk fill, group-masked loop) are built for the shapes the
+ * defaults pick for the BASELINE configurations only */
+#define ALT_COMBOS(X) X(8, 3, 2) X(8, 2, 2) X(16, 3, 4) X(16, 2, 4) X(16, 1, 2)
 
 static bool fast_combo(int G, int W, int L)
 {
@@ -951,6 +1170,20 @@ extern "C" int fsk_b200_cuda_find_frame_batch(void *p, const fsk_b200_geom *g, c
     return 0;
 }
 
+template <int G, int W, int L>
+static cudaError_t launch_rx_ws_t(const Shape &sh, const CudaEngine *ce, const fsk_b200_loopc *lc,
+	const RxArgs &a, cudaStream_t st)
+{
+    cudaError_t e = cudaFuncSetAttribute(k_rx_ws<G, W, L>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	    (int)sh.smem);
+    if (e != cudaSuccess)
+	return e;
+    k_rx_ws<G, W, L><<<sh.blocks, sh.wpb * 32, sh.smem, st>>>(sh.geo, *lc, ce->d_tw, sh.ring,
+	    sh.lookahead, a);
+    g_launches++;
+    return cudaGetLastError();
+}
+
 template <int G, int W, int L, int MODE, int FILL>
 static cudaError_t launch_rx_t(const Shape &sh, const CudaEngine *ce, const fsk_b200_loopc *lc,
 	const RxArgs &a, cudaStream_t st)
@@ -985,12 +1218,22 @@ extern "C" int fsk_b200_cuda_rx_batch(void *p, const fsk_b200_geom *g, const fsk
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e = cudaErrorInvalidValue;
     if (sh.mode == 0) {
-	if (ce->fill == 0) {
-#define X(GG, WW, LL) if (sh.G == GG && sh.W == WW && sh.L == LL) e = launch_rx_t<GG, WW, LL, 0, 0>(sh, ce, lc, a, st);
-	    FAST_COMBOS(X)
+	/* FSK_B200_FILL: 0 (default) cp.async fill, group-masked loop; 1 TMA bulk copies
+	 * (UBLKCP + mbarrier); 3 cp.async fill, warp-synchronous loop.  The two alternatives
+	 * pass the same tests and measured slower (profiles/README.md); they are built for the
+	 * shapes of the BASELINE configurations only. */
+	bool launched = false;
+	if (ce->fill == 1) {
+#define X(GG, WW, LL) if (sh.G == GG && sh.W == WW && sh.L == LL) { e = launch_rx_t<GG, WW, LL, 0, 1>(sh, ce, lc, a, st); launched = true; }
+	    ALT_COMBOS(X)
 #undef X
-	} else {
-#define X(GG, WW, LL) if (sh.G == GG && sh.W == WW && sh.L == LL) e = launch_rx_t<GG, WW, LL, 0, 1>(sh, ce, lc, a, st);
+	} else if (ce->fill == 3) {
+#define X(GG, WW, LL) if (sh.G == GG && sh.W == WW && sh.L == LL) { e = launch_rx_ws_t<GG, WW, LL>(sh, ce, lc, a, st); launched = true; }
+	    ALT_COMBOS(X)
+#undef X
+	}
+	if (!launched) {
+#define X(GG, WW, LL) if (sh.G == GG && sh.W == WW && sh.L == LL) e = launch_rx_t<GG, WW, LL, 0, 0>(sh, ce, lc, a, st);
 	    FAST_COMBOS(X)
 #undef X
 	}
