@@ -274,10 +274,17 @@ __device__ __forceinline__ unsigned ring_wrap(unsigned off, unsigned R) { return
 __device__ __forceinline__ float fast_sqrt(float x)
 {
     float r;
-    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
-__device__ __forceinline__ float fast_div(float a, float b) { return __fdividef(a, b); }
+__device__ __forceinline__ float fast_div(float a, float b)
+{
+    /* .ftz: two instructions (MUFU.RCP + FMUL) instead of the denormal-safe sequence; the
+     * operands are magnitudes and their sums, far from the denormal range */
+    float r;
+    asm("div.approx.ftz.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
 
 /* butterfly all-reduce over the G lanes of a group (every lane ends with the total) */
 template <int G>

@@ -167,7 +167,10 @@ template <int G, int W, int L, int MODE, int FILL>
 #ifndef FSK_MINBLOCKS
 #define FSK_MINBLOCKS 4
 #endif
-__global__ void __launch_bounds__(128, FSK_MINBLOCKS)
+#ifndef FSK_MAXTHREADS
+#define FSK_MAXTHREADS 128
+#endif
+__global__ void __launch_bounds__(FSK_MAXTHREADS, FSK_MINBLOCKS)
 k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200_loopc lc,
 	const float4 *__restrict__ tw_global, unsigned tw_in_smem, unsigned ring_floats,
 	unsigned lookahead, const __grid_constant__ RxArgs a)
