@@ -31,13 +31,18 @@ struct oracle_fftwf_plan_s {
     cpx *cin;       /* nc, used when n is odd */
 };
 
-void *fftwf_malloc(size_t n)
+/* every buffer gets its own cache lines (128-byte aligned, padded to a multiple of 128):
+ * the multi-threaded CPU baseline runs one plan per thread and must not false-share */
+static void *alloc_lines(size_t n)
 {
     void *p = NULL;
-    if (posix_memalign(&p, 64, n ? n : 64) != 0)
+    n = (n + 127) & ~(size_t)127;
+    if (posix_memalign(&p, 128, n ? n : 128) != 0)
 	return NULL;
     return p;
 }
+
+void *fftwf_malloc(size_t n) { return alloc_lines(n); }
 
 void fftwf_free(void *p) { free(p); }
 
@@ -197,9 +202,10 @@ fftwf_plan fftwf_plan_many_dft_r2c(int rank, const int *n, int howmany,
     (void)inembed; (void)onembed; (void)idist; (void)odist; (void)flags;
     if (rank != 1 || howmany != 1 || istride != 1 || ostride != 1 || n[0] < 1)
 	return NULL;
-    struct oracle_fftwf_plan_s *pl = calloc(1, sizeof(*pl));
+    struct oracle_fftwf_plan_s *pl = alloc_lines(sizeof(*pl));
     if (!pl)
 	return NULL;
+    memset(pl, 0, sizeof(*pl));
     pl->n = n[0];
     pl->even = (pl->n % 2 == 0) && pl->n >= 2;
     pl->nc = pl->even ? pl->n / 2 : pl->n;
@@ -210,11 +216,11 @@ fftwf_plan fftwf_plan_many_dft_r2c(int rank, const int *n, int howmany,
     for (int i = 0; i < pl->nfac; i++)
 	if (pl->fac[2 * i] > maxp)
 	    maxp = pl->fac[2 * i];
-    pl->tw = malloc(sizeof(cpx) * (size_t)pl->nc);
-    pl->work = malloc(sizeof(cpx) * (size_t)pl->nc);
-    pl->scratch = malloc(sizeof(cpx) * (size_t)maxp);
-    pl->cin = malloc(sizeof(cpx) * (size_t)pl->nc);
-    pl->rtw = malloc(sizeof(cpx) * (size_t)(pl->n / 2 + 1));
+    pl->tw = alloc_lines(sizeof(cpx) * (size_t)pl->nc);
+    pl->work = alloc_lines(sizeof(cpx) * (size_t)pl->nc);
+    pl->scratch = alloc_lines(sizeof(cpx) * (size_t)maxp);
+    pl->cin = alloc_lines(sizeof(cpx) * (size_t)pl->nc);
+    pl->rtw = alloc_lines(sizeof(cpx) * (size_t)(pl->n / 2 + 1));
     if (!pl->tw || !pl->work || !pl->scratch || !pl->cin || !pl->rtw) {
 	fftwf_destroy_plan(pl);
 	return NULL;
