@@ -11,10 +11,10 @@
  *         one LDS.128 (twiddles) + W LDS.32 (samples) feed 4*W FMAs.  W, L are
  *         compile-time so accumulators and per-bit results stay in registers;
  *         frame statistics are butterfly-reduced over the group.
- *  GENERIC frame_analyze<G,Src> / find_frame: any source (ring with mask, or
- *         global memory), run-time window split, fp64 folding for very long
- *         windows.  Used when the windows do not fit shared memory (e.g. 0.5
- *         baud) and as the reference implementation of the fast path in tests.
+ *  GENERIC frame_analyze<G,Src> / find_frame: samples straight from global
+ *         memory, run-time window split, IEEE sqrt/div, the reference's serial
+ *         summation order, fp64 folding of the fp32 partial sums for very long
+ *         windows.  Used when the windows do not fit shared memory (e.g. 0.5 baud).
  *
  * All floating-point steps that decide anything follow the reference's order
  * (src/fsk.c:107-174, :178-446, :449-538); comments carry its line numbers.
@@ -115,13 +115,6 @@ __device__ __forceinline__ float confidence_from_scratch(float2 *scr, unsigned n
 /* ======================================================================== */
 /* GENERIC path                                                             */
 /* ======================================================================== */
-
-/* shared-memory ring addressed by absolute sample index (power-of-two size) */
-struct RingSrc {
-    const float *ring;
-    unsigned mask;
-    __device__ __forceinline__ float operator()(unsigned i) const { return ring[i & mask]; }
-};
 
 /* straight from global memory, zero beyond the valid length */
 struct GlobalSrc {

@@ -1,26 +1,34 @@
 /*
- * fsk_b200_kernels.cu -- CUDA side of the B200 FSK engine (sm_100a).
+ * fsk_b200_kernels.cu -- CUDA side of the B200 FSK engine (sm_100a): the kernels and
+ * their host-side launch logic.  The device functions are in fsk_b200_device.cuh.
  *
- * Work decomposition (DESIGN.md has the derivation):
- *   - one GROUP of G lanes (G = 2..32, a power of two) owns one audio stream;
- *     a warp therefore runs 32/G streams side by side;
- *   - the stream's samples live in a per-stream shared-memory RING indexed by
- *     the absolute sample index (ring[i & mask]); every input sample is fetched
- *     from HBM exactly once, 16 bytes per lane, and stays there while the
- *     candidate frame positions that cover it are searched;
- *   - inside a frame candidate the lanes of a group split the bit windows
- *     (and, when G > n_bits, the samples of a window) and correlate each window
- *     against the mark and space tones at the FFT-bin centre frequencies
- *     (exp(-2 pi i k n / fftsize), k = b_mark, b_space) -- the two bins the
- *     reference reads out of a full FFT (src/fsk.c:157-159);
- *   - confidence (src/fsk.c:271-342), the zig-zag search with early-out
- *     (src/fsk.c:477-502) and the rx-loop state machine
- *     (src/minimodem.c:1229-1407) run per group in registers, in the
- *     reference's order of floating-point operations.
+ * Work decomposition (DESIGN.md has the derivation and the measurements):
+ *   - one GROUP of G lanes (4, 8, 16 or 32) owns one audio stream; a warp runs 32/G
+ *     streams side by side; a block of `wpb` warps is the unit the hardware scheduler
+ *     hands out, so streams of different length or difficulty balance by themselves;
+ *   - the stream's samples live in a per-stream shared-memory RING (whole 128-float
+ *     blocks, the first bit-window length mirrored behind its end); every input sample
+ *     is fetched from HBM exactly once with 16-byte cp.async copies (or, selectably,
+ *     cp.async.bulk through the TMA engine) issued one loop iteration ahead of its use;
+ *   - inside a frame candidate the lanes of a group split the bit windows and, L lanes
+ *     per window, the samples of a window, and correlate each window against the mark
+ *     and space tones at the FFT-bin centre frequencies (exp(-2 pi i k n / fftsize),
+ *     k = b_mark, b_space) -- the two bins the reference reads out of a full FFT
+ *     (src/fsk.c:157-159);
+ *   - the frame statistic (src/fsk.c:271-342), the zig-zag search with early-out
+ *     (src/fsk.c:477-502) and the rx-loop state machine (src/minimodem.c:1229-1407)
+ *     run per group in registers.
  *
- * Compiled with -fmad=false: every a*b+c below is either an explicit fmaf()
- * (the correlation sums) or two separately rounded operations, as in the
- * reference's x86-64 build.
+ * k_rx<G,W,L,MODE,FILL>   the whole rx loop per stream (MODE 0 fast / 1 generic)
+ * k_rx_ws<G,W,L>          the same, warp-synchronous (selectable, measured slower)
+ * k_find_frame<G,W,L,MODE> batched fsk_find_frame
+ * k_tx, k_band_mags, k_s16_to_f32, k_decode_ascii   the "next" rows
+ *
+ * Compiled with -fmad=false: every a*b+c below is either an explicit fmaf() (the
+ * correlation sums) or two separately rounded operations, as in the reference's
+ * x86-64 build.  The generic path also keeps IEEE division and square root and the
+ * reference's serial summation order; the fast path uses approximate (<= 2 ulp)
+ * division/sqrt and a fixed tree order for the frame statistic.
  */
 #include <cuda_runtime.h>
 #include <errno.h>
