@@ -305,6 +305,43 @@ __device__ __forceinline__ unsigned group_add(unsigned v, unsigned gmask)
     return v;
 }
 
+/* What a lane needs to know about its W windows, computed once per kernel instead of per
+ * candidate: the offset of each window inside a frame candidate, which of them this lane
+ * post-processes, and the expected bit ('0', '1' or don't care) under both expect strings. */
+template <int W>
+struct LaneWin {
+    unsigned beg[W];	/* bit_begin of window j (0 for a slot past n_bits) */
+    unsigned own;	/* bit j: this lane decides window j */
+    unsigned exp;	/* 2 bits per (sel, j): expect value 0, 1 or 2 */
+};
+
+template <int G, int W, int L>
+__device__ __forceinline__ LaneWin<W> lane_windows(const fsk_b200_geom &geo, unsigned g)
+{
+    constexpr unsigned WPP = G / L;
+    const unsigned part = g % L, wslot = g / L;
+    LaneWin<W> lw;
+    lw.own = 0;
+    lw.exp = 0;
+#pragma unroll
+    for (int j = 0; j < W; j++) {
+	const unsigned w = j * WPP + wslot;
+	const bool valid = w < geo.n_bits;
+	lw.beg[j] = valid ? geo.bit_begin[w] : 0u;
+	if (valid && part == (unsigned)(j % L))
+	    lw.own |= 1u << j;
+	const unsigned e0 = valid ? geo.expect[0][w] : 2u, e1 = valid ? geo.expect[1][w] : 2u;
+	lw.exp |= (e0 << (2 * j)) | (e1 << (2 * (j + W)));
+    }
+    return lw;
+}
+
+/* best candidate of a search (src/fsk.c:504-508), returned in registers */
+struct Found {
+    float confidence, amplitude;
+    unsigned start, bits_lo, bits_hi;
+};
+
 /* One candidate frame start, fast path.  Lane g of the group owns the windows
  * w = j*(G/L) + g/L (j < W) and, of each, the samples n = g%L, g%L + L, ...
  * Everything stays in registers: the per-bit (sig, noise, bit) values never go
@@ -313,8 +350,8 @@ __device__ __forceinline__ unsigned group_add(unsigned v, unsigned gmask)
  * (same terms, different but fixed summation order). */
 template <int G, int W, int L, bool WS = false>
 __device__ __forceinline__ float frame_analyze_fast(const Ring rg, unsigned cand_off,
-	const fsk_b200_geom &geo, int sel, unsigned tw_s,
-	unsigned g, unsigned gmask_in, unsigned long long &bits_out, float &ampl_out)
+	const fsk_b200_geom &geo, const LaneWin<W> &lw, int sel, unsigned tw_s,
+	unsigned g, unsigned gmask_in, unsigned &bits_lo_out, unsigned &bits_hi_out, float &ampl_out)
 {
     /* WS ("warp-synchronous"): the caller guarantees that all 32 lanes are here together, so
      * shuffles and votes use the constant full mask (the shuffle distances stay inside a
@@ -335,10 +372,8 @@ __device__ __forceinline__ float frame_analyze_fast(const Ring rg, unsigned cand
     /* slots past n_bits read window 0: harmless, their results are dropped */
     const float *p[W];
 #pragma unroll
-    for (int j = 0; j < W; j++) {
-	const unsigned w = j * WPP + wslot;
-	p[j] = ring + ring_wrap(cand_off + (w < nb ? geo.bit_begin[w] : 0u), R);
-    }
+    for (int j = 0; j < W; j++)
+	p[j] = ring + ring_wrap(cand_off + lw.beg[j], R);
 
     float acc[W][4];
 #pragma unroll
@@ -384,7 +419,7 @@ __device__ __forceinline__ float frame_analyze_fast(const Ring rg, unsigned cand
 #pragma unroll
     for (int j = 0; j < W; j++) {
 	const unsigned w = j * WPP + wslot;
-	own[j] = w < nb && part == (unsigned)(j % L);	/* after the butterfly every lane of the window has the sums */
+	own[j] = (lw.own >> j) & 1u;	/* after the butterfly every lane of the window has the sums */
 	sig[j] = 0.f;
 	one[j] = false;
 	if (own[j]) {
@@ -409,7 +444,7 @@ __device__ __forceinline__ float frame_analyze_fast(const Ring rg, unsigned cand
 	    one[j] = mag_mark > mag_space;			/* strict: tie -> space */
 	    sig[j] = one[j] ? mag_mark : mag_space;
 	    const float noise = one[j] ? mag_space : mag_mark;
-	    const unsigned e = geo.expect[sel][w];
+	    const unsigned e = (lw.exp >> (2 * (j + (sel ? W : 0)))) & 3u;
 	    mismatch |= e != 2u && e != (one[j] ? 1u : 0u);	/* pass 1, :211 */
 	    if (noise > FSK_FLT_EPSILON)			/* :279 */
 		tn += noise;
@@ -426,7 +461,7 @@ __device__ __forceinline__ float frame_analyze_fast(const Ring rg, unsigned cand
     const bool rejected = WS ? (__ballot_sync(0xffffffffu, mismatch) & gmask_in) != 0u
 			     : __any_sync(gmask, mismatch) != 0;
     if (!WS && rejected) {
-	bits_out = 0;
+	bits_lo_out = bits_hi_out = 0;
 	ampl_out = 0.f;
 	return 0.f;
     }
@@ -467,11 +502,12 @@ __device__ __forceinline__ float frame_analyze_fast(const Ring rg, unsigned cand
     divergence = fast_div(divergence, (float)(int)nb);
 
     if (WS && rejected) {
-	bits_out = 0;
+	bits_lo_out = bits_hi_out = 0;
 	ampl_out = 0.f;
 	return 0.f;
     }
-    bits_out = ((unsigned long long)bhi << 32) | blo;
+    bits_lo_out = blo;
+    bits_hi_out = bhi;
     ampl_out = avg_bit_sig;					/* :342 */
     return snr * (1.0f - divergence);				/* :336 */
 }
@@ -481,15 +517,11 @@ __device__ __forceinline__ float frame_analyze_fast(const Ring rg, unsigned cand
  * false) rides along on candidate 0 and drops the result.  SIMT would spend those trips
  * waiting anyway; in exchange all shuffles inside use the constant full mask. */
 template <int G, int W, int L>
-__device__ __noinline__ float find_frame_ws(const Ring rg, unsigned pos_off,
-	const fsk_b200_geom &geo, int sel, unsigned tw_s, unsigned g, unsigned gmask, bool on,
-	unsigned try_first, unsigned try_max, unsigned try_step, float limit,
-	unsigned long long &best_bits, float &best_a, unsigned &best_t)
+__device__ __noinline__ Found find_frame_ws(const Ring rg, unsigned pos_off,
+	const fsk_b200_geom &geo, const LaneWin<W> lw, int sel, unsigned tw_s, unsigned g,
+	unsigned gmask, bool on, unsigned try_first, unsigned try_max, unsigned try_step, float limit)
 {
-    float best_c = 0.f;
-    best_t = 0;
-    best_a = 0.f;
-    best_bits = 0;
+    Found best = { 0.f, 0.f, 0u, 0u, 0u };
     bool searching = on;
     for (int j = 0; __any_sync(0xffffffffu, searching); j++) {
 	const int up = (j & 1) ? 1 : -1;
@@ -497,32 +529,44 @@ __device__ __noinline__ float find_frame_ws(const Ring rg, unsigned pos_off,
 	if (t >= (int)try_max)
 	    searching = false;					/* :481 */
 	const bool eval = searching && t >= 0;			/* :483 */
-	unsigned long long bits;
+	unsigned lo, hi;
 	float a;
 	const float c = frame_analyze_fast<G, W, L, true>(rg, eval ? ring_wrap(pos_off + (unsigned)t, rg.R) : 0u,
-		geo, sel, tw_s, g, gmask, bits, a);
-	if (eval && best_c < c) {				/* :492: NaN and negatives never win */
-	    best_t = (unsigned)t;
-	    best_c = c;
-	    best_a = a;
-	    best_bits = bits;
-	    if (best_c >= limit)
+		geo, lw, sel, tw_s, g, gmask, lo, hi, a);
+	if (eval && best.confidence < c) {			/* :492: NaN and negatives never win */
+	    best = Found{ c, a, (unsigned)t, lo, hi };
+	    if (c >= limit)
 		searching = false;				/* :499 first to reach the limit wins */
 	}
     }
-    return best_c;
+    return best;
 }
 
+/* frame search, src/fsk.c:449-538 */
 template <int G, int W, int L>
-__device__ __noinline__ float find_frame_fast(const Ring rg, unsigned pos_off,
-	const fsk_b200_geom &geo, int sel, unsigned tw_s,
-	unsigned g, unsigned gmask, unsigned try_first, unsigned try_max, unsigned try_step,
-	float limit, unsigned long long &best_bits, float &best_a, unsigned &best_t)
+__device__ __noinline__ Found find_frame_fast(const Ring rg, unsigned pos_off,
+	const fsk_b200_geom &geo, const LaneWin<W> lw, int sel, unsigned tw_s,
+	unsigned g, unsigned gmask, unsigned try_first, unsigned try_max, unsigned try_step, float limit)
 {
-    return search_frames([&](unsigned t, unsigned long long &bits, float &a) {
-	return frame_analyze_fast<G, W, L>(rg, ring_wrap(pos_off + t, rg.R), geo, sel, tw_s,
-		g, gmask, bits, a);
-    }, try_first, try_max, try_step, limit, best_bits, best_a, best_t);
+    Found best = { 0.f, 0.f, 0u, 0u, 0u };
+    for (int j = 0;; j++) {					/* :477-502 */
+	const int up = (j & 1) ? 1 : -1;
+	const int t = (int)try_first + up * ((j + 1) / 2) * (int)try_step;
+	if (t >= (int)try_max)
+	    break;
+	if (t < 0)
+	    continue;
+	unsigned lo, hi;
+	float a;
+	const float c = frame_analyze_fast<G, W, L>(rg, ring_wrap(pos_off + (unsigned)t, rg.R), geo, lw, sel,
+		tw_s, g, gmask, lo, hi, a);
+	if (best.confidence < c) {			/* NaN and negatives never win */
+	    best = Found{ c, a, (unsigned)t, lo, hi };
+	    if (c >= limit)
+		break;				/* first to reach the limit wins */
+	}
+    }
+    return best;
 }
 
 /* ------------------------------------------------------------------------ */

@@ -129,6 +129,7 @@ k_find_frame(const __grid_constant__ fsk_b200_geom geo, const float4 *__restrict
     GROUP_VARS;
     const Ring rg = { smem_u32(sm.ring), ring_floats, (geo.bit_nsamples + 3u) & ~3u };
     const unsigned tw_s = tw_in_smem ? smem_u32(sm.tw) : 0u;	/* the fast path requires the table in shared memory */
+    const LaneWin<W> lw = lane_windows<G, W, L>(geo, g);
 
     for (unsigned s = (blockIdx.x * wpb + warp) * spw + sidx; s < a.nstreams;
 	    s += gridDim.x * wpb * spw) {
@@ -152,8 +153,12 @@ k_find_frame(const __grid_constant__ fsk_b200_geom geo, const float4 *__restrict
 		cp_async_commit();
 		cp_async_wait<0>();
 		__syncwarp(gmask);
-		conf = find_frame_fast<G, W, L>(rg, off & 3u, geo, sel, tw_s, g, gmask,
-			a.try_first[s], tmax, tstep, a.limit[s], bits, ampl, start);
+		const Found f = find_frame_fast<G, W, L>(rg, off & 3u, geo, lw, sel, tw_s, g, gmask,
+			a.try_first[s], tmax, tstep, a.limit[s]);
+		conf = f.confidence;
+		ampl = f.amplitude;
+		start = f.start;
+		bits = ((unsigned long long)f.bits_hi << 32) | f.bits_lo;
 	    } else {
 		const GlobalSrc src = { x, n };
 		conf = find_frame<G, GlobalSrc>(src, off, geo, sel, sm.tw, sm.scr, g, gmask,
@@ -188,6 +193,7 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
     GROUP_VARS;
     const Ring rg = { smem_u32(sm.ring), ring_floats, (geo.bit_nsamples + 3u) & ~3u };
     const unsigned tw_s = tw_in_smem ? smem_u32(sm.tw) : 0u;	/* the fast path requires the table in shared memory */
+    const LaneWin<W> lw = lane_windows<G, W, L>(geo, g);
     const unsigned R = ring_floats;
 
     for (unsigned s = (blockIdx.x * wpb + warp) * spw + sidx; s < a.nstreams;
@@ -223,16 +229,22 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
 	/* request the ring content up to absolute index `to` (rounded up to whole blocks) */
 	auto request = [&](unsigned to) {
 	    if (FILL == 0) {
+		/* whole blocks up to `to`, never past what the ring can hold */
 		const unsigned cap = (pos & ~3u) + R;
-		while (filled < to && filled + RING_BLOCK <= cap) {
-		    if (filled + RING_BLOCK <= n)
+		unsigned nblk = to > filled ? (to - filled + RING_BLOCK - 1u) / RING_BLOCK : 0u;
+		nblk = min(nblk, (cap - filled) / RING_BLOCK);
+		if (filled + nblk * RING_BLOCK <= n) {
+		    for (; nblk; nblk--) {			/* the common case: all of it valid */
 			ring_block<G>(rg, ring_s, foff, x + filled, g);
-		    else
+			filled += RING_BLOCK;
+			foff = foff + RING_BLOCK == R ? 0u : foff + RING_BLOCK;
+		    }
+		} else {
+		    for (; nblk; nblk--) {			/* end of the stream: zero fill */
 			ring_block_tail<G>(rg, ring_s, foff, x, n, filled, g);
-		    filled += RING_BLOCK;
-		    foff += RING_BLOCK;
-		    if (foff >= R)
-			foff = 0;
+			filled += RING_BLOCK;
+			foff = foff + RING_BLOCK == R ? 0u : foff + RING_BLOCK;
+		    }
 		}
 		cp_async_commit();
 	    } else {
@@ -330,11 +342,14 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
 	    unsigned long long bits;
 	    float amplitude, confidence;
 	    unsigned frame_start;
-	    if (MODE == 0)
-		confidence = find_frame_fast<G, W, L>(rg, pos_off, geo, sel, tw_s, g, gmask,
-			try_first, try_max, try_step, lc.confidence_search_limit,
-			bits, amplitude, frame_start);		/* :1265 */
-	    else
+	    if (MODE == 0) {
+		const Found f = find_frame_fast<G, W, L>(rg, pos_off, geo, lw, sel, tw_s, g, gmask,
+			try_first, try_max, try_step, lc.confidence_search_limit);	/* :1265 */
+		confidence = f.confidence;
+		amplitude = f.amplitude;
+		frame_start = f.start;
+		bits = ((unsigned long long)f.bits_hi << 32) | f.bits_lo;
+	    } else
 		confidence = find_frame<G, GlobalSrc>(gsrc, pos, geo, sel, sm.tw, sm.scr, g, gmask,
 			try_first, try_max, try_step, lc.confidence_search_limit,
 			bits, amplitude, frame_start);
@@ -384,11 +399,14 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
 		    float amplitude2, confidence2;
 		    unsigned frame_start2;
 		    /* `carrier` is 1 by now, so the data string is searched (:1378) */
-		    if (MODE == 0)
-			confidence2 = find_frame_fast<G, W, L>(rg, pos_off, geo, 0, tw_s, g,
-				gmask, try_first, try_max, try_step, INFINITY,
-				bits2, amplitude2, frame_start2);
-		    else
+		    if (MODE == 0) {
+			const Found f = find_frame_fast<G, W, L>(rg, pos_off, geo, lw, 0, tw_s, g,
+				gmask, try_first, try_max, try_step, INFINITY);
+			confidence2 = f.confidence;
+			amplitude2 = f.amplitude;
+			frame_start2 = f.start;
+			bits2 = ((unsigned long long)f.bits_hi << 32) | f.bits_lo;
+		    } else
 			confidence2 = find_frame<G, GlobalSrc>(gsrc, pos, geo, 0, sm.tw, sm.scr, g,
 				gmask, try_first, try_max, try_step, INFINITY,
 				bits2, amplitude2, frame_start2);
@@ -462,6 +480,7 @@ k_rx_ws(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b
     GROUP_VARS;
     const Ring rg = { smem_u32(sm.ring), ring_floats, (geo.bit_nsamples + 3u) & ~3u };
     const unsigned tw_s = smem_u32(sm.tw);
+    const LaneWin<W> lw = lane_windows<G, W, L>(geo, g);
     const unsigned R = ring_floats;
     const unsigned FULL = 0xffffffffu;
     const unsigned need_max = lc.try_max_nocarrier - 1u + geo.span;
@@ -543,12 +562,12 @@ k_rx_ws(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b
 		cp_async_wait<1>();
 	    __syncwarp();
 
-	    unsigned long long bits;
-	    float amplitude;
-	    unsigned frame_start;
-	    float confidence = find_frame_ws<G, W, L>(rg, pos_off, geo, sel, tw_s, g, gmask, alive,
-		    try_first, try_max, try_step, lc.confidence_search_limit,
-		    bits, amplitude, frame_start);		/* :1265 */
+	    const Found f1 = find_frame_ws<G, W, L>(rg, pos_off, geo, lw, sel, tw_s, g, gmask, alive,
+		    try_first, try_max, try_step, lc.confidence_search_limit);	/* :1265 */
+	    unsigned long long bits = ((unsigned long long)f1.bits_hi << 32) | f1.bits_lo;
+	    float amplitude = f1.amplitude;
+	    unsigned frame_start = f1.start;
+	    float confidence = f1.confidence;
 
 	    bool want_refine = false;
 	    if (confidence < peak_confidence * 0.75f) {		/* :1278-1282 */
@@ -595,16 +614,13 @@ k_rx_ws(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b
 		unsigned fine_step = try_max / 8u;
 		if (fine_step == 0)
 		    fine_step = 1;
-		unsigned long long bits2;
-		float amplitude2;
-		unsigned frame_start2;
 		/* `carrier` is 1 by now, so the data string is searched (:1378) */
-		const float confidence2 = find_frame_ws<G, W, L>(rg, pos_off, geo, 0, tw_s, g, gmask, refine,
-			try_first, try_max, fine_step, INFINITY, bits2, amplitude2, frame_start2);
-		if (refine && confidence2 > confidence) {
-		    bits = bits2;
-		    amplitude = amplitude2;
-		    frame_start = frame_start2;
+		const Found f2 = find_frame_ws<G, W, L>(rg, pos_off, geo, lw, 0, tw_s, g, gmask, refine,
+			try_first, try_max, fine_step, INFINITY);
+		if (refine && f2.confidence > confidence) {
+		    bits = ((unsigned long long)f2.bits_hi << 32) | f2.bits_lo;
+		    amplitude = f2.amplitude;
+		    frame_start = f2.start;
 		}
 	    }
 	    if (confident) {
