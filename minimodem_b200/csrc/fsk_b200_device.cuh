@@ -410,23 +410,40 @@ __device__ __forceinline__ float frame_analyze_fast(const Ring rg, unsigned cand
 	}
     }
 
-    /* per-window decision (src/fsk.c:158-169) and this lane's share of the sums (:271-289) */
-    float ts = 0.f, tn = 0.f, am = 0.f, as = 0.f;
+    /* per-window decision (src/fsk.c:158-169) and this lane's share of the sums (:271-289).
+     * After the butterfly all L lanes of a window hold its sums, so they share the work:
+     * lane part p decides the windows j = p, p+L, ... (KW = ceil(W/L) rounds instead of W).
+     * Magnitudes stay unscaled (the 2/N of src/fsk.c:132 is applied once, to the amplitude);
+     * the FLT_EPSILON threshold of :279 is scaled the other way instead. */
+    constexpr int KW = (W + L - 1) / L;
+    const float eps_u = geo.eps_unscaled;
+    float tn = 0.f, am = 0.f, as = 0.f;
     unsigned nm = 0, blo = 0, bhi = 0;
-    float sig[W];
-    bool one[W], own[W];
+    float sig[KW];
+    bool one[KW], own[KW];
     bool mismatch = false;
 #pragma unroll
-    for (int j = 0; j < W; j++) {
-	const unsigned w = j * WPP + wslot;
-	own[j] = (lw.own >> j) & 1u;	/* after the butterfly every lane of the window has the sums */
-	sig[j] = 0.f;
-	one[j] = false;
-	if (own[j]) {
-	    float mag_mark = fast_sqrt(acc[j][0] * acc[j][0] + acc[j][1] * acc[j][1]) * geo.mag_scalar;
-	    float mag_space = fast_sqrt(acc[j][2] * acc[j][2] + acc[j][3] * acc[j][3]) * geo.mag_scalar;
-	    if (needs_resum(mag_mark, mag_space)) {
-		const float *q = p[j];
+    for (int k = 0; k < KW; k++) {
+	const unsigned jsel = part + (unsigned)(k * L);		/* this lane's window in round k */
+	float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+	const float *q = p[0];
+#pragma unroll
+	for (int pp = 0; pp < L; pp++) {
+	    constexpr int dummy = 0; (void)dummy;
+	    const int j = pp + k * L;
+	    if (j < W && part == (unsigned)pp) {
+		a0 = acc[j][0]; a1 = acc[j][1]; a2 = acc[j][2]; a3 = acc[j][3];
+		q = p[j];
+	    }
+	}
+	own[k] = (lw.own >> jsel) & 1u;
+	sig[k] = 0.f;
+	one[k] = false;
+	if (own[k]) {
+	    float mag_mark = fast_sqrt(a0 * a0 + a1 * a1);
+	    float mag_space = fast_sqrt(a2 * a2 + a3 * a3);
+	    if (fminf(mag_mark, mag_space) < eps_u + 2e-6f * fmaxf(mag_mark, mag_space)) {
+		/* too close to the :279 threshold for fp32 sums (see needs_resum): fp64 re-sum */
 		double drm = 0., dim = 0., drs = 0., dis = 0.;
 #pragma unroll 1
 		for (unsigned i = 0; i < N; i++) {
@@ -438,22 +455,23 @@ __device__ __forceinline__ float frame_analyze_fast(const Ring rg, unsigned cand
 		    dis = fma(x, (double)c.w, dis);
 		}
 		const float frm = (float)drm, fim = (float)dim, frs = (float)drs, fis = (float)dis;
-		mag_mark = sqrtf(frm * frm + fim * fim) * geo.mag_scalar;
-		mag_space = sqrtf(frs * frs + fis * fis) * geo.mag_scalar;
+		mag_mark = sqrtf(frm * frm + fim * fim);
+		mag_space = sqrtf(frs * frs + fis * fis);
 	    }
-	    one[j] = mag_mark > mag_space;			/* strict: tie -> space */
-	    sig[j] = one[j] ? mag_mark : mag_space;
-	    const float noise = one[j] ? mag_space : mag_mark;
-	    const unsigned e = (lw.exp >> (2 * (j + (sel ? W : 0)))) & 3u;
-	    mismatch |= e != 2u && e != (one[j] ? 1u : 0u);	/* pass 1, :211 */
-	    if (noise > FSK_FLT_EPSILON)			/* :279 */
+	    const unsigned w = jsel * WPP + wslot;
+	    one[k] = mag_mark > mag_space;			/* strict: tie -> space */
+	    sig[k] = one[k] ? mag_mark : mag_space;
+	    const float noise = one[k] ? mag_space : mag_mark;
+	    const unsigned e = (lw.exp >> (2u * (jsel + (sel ? (unsigned)W : 0u)))) & 3u;
+	    mismatch |= e != 2u && e != (one[k] ? 1u : 0u);	/* pass 1, :211 */
+	    if (noise > eps_u)					/* :279 */
 		tn += noise;
-	    if (one[j]) {
-		am += sig[j];
+	    if (one[k]) {
+		am += sig[k];
 		nm++;
 		if (w < 32u) blo |= 1u << w; else bhi |= 1u << (w - 32u);
 	    } else {
-		as += sig[j];
+		as += sig[k];
 	    }
 	}
     }
@@ -470,7 +488,7 @@ __device__ __forceinline__ float frame_analyze_fast(const Ring rg, unsigned cand
     tn = group_sum<G>(tn, gmask);
     am = group_sum<G>(am, gmask);
     as = group_sum<G>(as, gmask);
-    ts = am + as;
+    const float ts = am + as;
     if (nb <= 24u) {
 	const unsigned packed = group_add<G>(blo | (nm << 24), gmask);
 	blo = packed & 0xffffffu;
@@ -484,22 +502,22 @@ __device__ __forceinline__ float frame_analyze_fast(const Ring rg, unsigned cand
 
     const unsigned n_space = nb - nm;
     const float snr = fast_div(ts, tn);					/* :292, may be +inf */
-    const float avg_bit_sig = fast_div(ts, (float)(int)nb);		/* :295 */
+    const float avg_bit_sig = ts * geo.inv_n_bits * geo.mag_scalar;	/* :295, with the 2/N of :132 */
     if (nm)
 	am = fast_div(am, (float)nm);					/* :298-301 */
     if (n_space)
 	as = fast_div(as, (float)n_space);
     float dv = 0.f;						/* :305-311 */
 #pragma unroll
-    for (int j = 0; j < W; j++) {
-	if (own[j]) {
-	    const float other = one[j] ? am : as;
-	    dv += fast_div(fabsf(sig[j] - other), other);
+    for (int k = 0; k < KW; k++) {
+	if (own[k]) {
+	    const float other = one[k] ? am : as;
+	    dv += fast_div(fabsf(sig[k] - other), other);
 	}
     }
     float divergence = group_sum<G>(dv, gmask);
     divergence *= 2.f;						/* :312-313 */
-    divergence = fast_div(divergence, (float)(int)nb);
+    divergence = divergence * geo.inv_n_bits;
 
     if (WS && rejected) {
 	bits_lo_out = bits_hi_out = 0;

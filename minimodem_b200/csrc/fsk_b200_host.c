@@ -213,6 +213,8 @@ int fsk_b200_geom_from(unsigned int frame_nsamples, const char *expect_data,
 	g->bit_begin[b] = (float)(spb * (int)b + 0.5f);	/* src/fsk.c:204,249 */
     g->span = g->bit_begin[g->n_bits - 1] + g->bit_nsamples;
     g->mag_scalar = 2.0f / (float)g->bit_nsamples;	/* src/fsk.c:132 */
+    g->eps_unscaled = 1.1920928955078125e-07f / g->mag_scalar;
+    g->inv_n_bits = 1.0f / (float)(int)g->n_bits;
     g->lanes_per_window = 1;
     for (int k = 0; k < 2; k++) {
 	const char *e = k ? (expect_sync ? expect_sync : expect_data) : expect_data;

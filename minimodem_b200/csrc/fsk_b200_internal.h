@@ -20,6 +20,8 @@ typedef struct fsk_b200_geom {
     unsigned int span;			/* bit_begin[n_bits-1] + bit_nsamples */
     unsigned int lanes_per_window;	/* filled in at launch */
     float	mag_scalar;		/* 2.0f / bit_nsamples, src/fsk.c:132 */
+    float	eps_unscaled;		/* FLT_EPSILON / mag_scalar: the :279 threshold before scaling */
+    float	inv_n_bits;		/* 1.0f / n_bits */
     unsigned int bit_begin[FSK_B200_MAX_BITS];
     unsigned char expect[2][FSK_B200_MAX_BITS];	/* [0]=data [1]=sync; 0,1 or 2 ('d') */
 } fsk_b200_geom;
