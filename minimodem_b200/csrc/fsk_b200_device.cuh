@@ -305,6 +305,10 @@ __device__ __forceinline__ unsigned group_add(unsigned v, unsigned gmask)
     return v;
 }
 
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int NKEEP>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" :: "n"(NKEEP) : "memory"); }
+
 /* What a lane needs to know about its W windows, computed once per kernel instead of per
  * candidate: the offset of each window inside a frame candidate, which of them this lane
  * post-processes, and the expected bit ('0', '1' or don't care) under both expect strings. */
@@ -313,7 +317,19 @@ struct LaneWin {
     unsigned beg[W];	/* bit_begin of window j (0 for a slot past n_bits) */
     unsigned own;	/* bit j: this lane decides window j */
     unsigned exp;	/* 2 bits per (sel, j): expect value 0, 1 or 2 */
+    unsigned a_end;	/* samples of a candidate that the first stage (windows j < STAGE_J) reads */
 };
+
+/* The correlation of a candidate can run in two stages: the windows j < FSK_STAGE_J of every
+ * lane (the first FSK_STAGE_J*G/L bits of the frame), then the rest.  The rx loop asks for the
+ * tail of a frame's samples only when it gets there, so a first stage could work on samples
+ * already in the ring while the copies of the rest are in flight.  Measured: the second
+ * twiddle pass costs more than the hidden latency buys (-4.5 % at stage 1, -6 % at stage 2),
+ * so the default is one stage (any value >= W); the wait still sits inside the search, right
+ * before the first candidate's correlation. */
+#ifndef FSK_STAGE_J
+#define FSK_STAGE_J 99
+#endif
 
 template <int G, int W, int L>
 __device__ __forceinline__ LaneWin<W> lane_windows(const fsk_b200_geom &geo, unsigned g)
@@ -323,6 +339,10 @@ __device__ __forceinline__ LaneWin<W> lane_windows(const fsk_b200_geom &geo, uns
     LaneWin<W> lw;
     lw.own = 0;
     lw.exp = 0;
+    {
+	const unsigned na = min((unsigned)FSK_STAGE_J * WPP, geo.n_bits);
+	lw.a_end = geo.bit_begin[na - 1u] + geo.bit_nsamples;
+    }
 #pragma unroll
     for (int j = 0; j < W; j++) {
 	const unsigned w = j * WPP + wslot;
@@ -334,6 +354,31 @@ __device__ __forceinline__ LaneWin<W> lane_windows(const fsk_b200_geom &geo, uns
 	lw.exp |= (e0 << (2 * j)) | (e1 << (2 * (j + W)));
     }
     return lw;
+}
+
+/* windows J0..J1-1 of this lane against both tones, its share n = part, part+L, ... of the samples */
+template <int J0, int J1, int W, int L>
+__device__ __forceinline__ void corr_pass(float (&acc)[W][4], const float *const (&p)[W],
+	const float4 *tw, unsigned part, unsigned N)
+{
+#if defined(FSK_UNROLL) && FSK_UNROLL == 8
+    _Pragma("unroll 8")
+#elif defined(FSK_UNROLL) && FSK_UNROLL == 2
+    _Pragma("unroll 2")
+#else
+    _Pragma("unroll 4")
+#endif
+    for (unsigned n = part; n < N; n += L) {
+	const float4 c = tw[n];
+#pragma unroll
+	for (int j = J0; j < J1; j++) {
+	    const float x = p[j][n];
+	    acc[j][0] = fmaf(x, c.x, acc[j][0]);
+	    acc[j][1] = fmaf(x, c.y, acc[j][1]);
+	    acc[j][2] = fmaf(x, c.z, acc[j][2]);
+	    acc[j][3] = fmaf(x, c.w, acc[j][3]);
+	}
+    }
 }
 
 /* best candidate of a search (src/fsk.c:504-508), returned in registers */
@@ -351,7 +396,8 @@ struct Found {
 template <int G, int W, int L, bool WS = false>
 __device__ __forceinline__ float frame_analyze_fast(const Ring rg, unsigned cand_off,
 	const fsk_b200_geom &geo, const LaneWin<W> &lw, int sel, unsigned tw_s,
-	unsigned g, unsigned gmask_in, unsigned &bits_lo_out, unsigned &bits_hi_out, float &ampl_out)
+	unsigned g, unsigned gmask_in, unsigned &bits_lo_out, unsigned &bits_hi_out, float &ampl_out,
+	int avail, bool &pending)
 {
     /* WS ("warp-synchronous"): the caller guarantees that all 32 lanes are here together, so
      * shuffles and votes use the constant full mask (the shuffle distances stay inside a
@@ -380,24 +426,23 @@ __device__ __forceinline__ float frame_analyze_fast(const Ring rg, unsigned cand
     for (int j = 0; j < W; j++)
 	acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
 
-#if defined(FSK_UNROLL) && FSK_UNROLL == 8
-    _Pragma("unroll 8")
-#elif defined(FSK_UNROLL) && FSK_UNROLL == 2
-    _Pragma("unroll 2")
-#else
-    _Pragma("unroll 4")
-#endif
-    for (unsigned n = part; n < N; n += L) {
-	const float4 c = tw[n];
-#pragma unroll
-	for (int j = 0; j < W; j++) {
-	    const float x = p[j][n];
-	    acc[j][0] = fmaf(x, c.x, acc[j][0]);
-	    acc[j][1] = fmaf(x, c.y, acc[j][1]);
-	    acc[j][2] = fmaf(x, c.z, acc[j][2]);
-	    acc[j][3] = fmaf(x, c.w, acc[j][3]);
+    /* `pending`: copies into this ring may still be in flight; `avail` samples from the
+     * candidate's first one are known to have landed */
+    constexpr int SJ = (FSK_STAGE_J < W) ? FSK_STAGE_J : 0;
+    if (SJ > 0) {
+	if (pending && (int)lw.a_end > avail) {
+	    cp_async_wait<0>();
+	    __syncwarp(gmask);
+	    pending = false;
 	}
+	corr_pass<0, SJ, W, L>(acc, p, tw, part, N);
     }
+    if (pending) {
+	cp_async_wait<0>();
+	__syncwarp(gmask);
+	pending = false;
+    }
+    corr_pass<SJ, W, W, L>(acc, p, tw, part, N);
     if (L > 1) {
 #pragma unroll
 	for (int o = L >> 1; o; o >>= 1) {
@@ -540,7 +585,7 @@ __device__ __noinline__ Found find_frame_ws(const Ring rg, unsigned pos_off,
 	unsigned gmask, bool on, unsigned try_first, unsigned try_max, unsigned try_step, float limit)
 {
     Found best = { 0.f, 0.f, 0u, 0u, 0u };
-    bool searching = on;
+    bool searching = on, nopend = false;
     for (int j = 0; __any_sync(0xffffffffu, searching); j++) {
 	const int up = (j & 1) ? 1 : -1;
 	const int t = (int)try_first + up * ((j + 1) / 2) * (int)try_step;
@@ -550,7 +595,7 @@ __device__ __noinline__ Found find_frame_ws(const Ring rg, unsigned pos_off,
 	unsigned lo, hi;
 	float a;
 	const float c = frame_analyze_fast<G, W, L, true>(rg, eval ? ring_wrap(pos_off + (unsigned)t, rg.R) : 0u,
-		geo, lw, sel, tw_s, g, gmask, lo, hi, a);
+		geo, lw, sel, tw_s, g, gmask, lo, hi, a, 0, nopend);
 	if (eval && best.confidence < c) {			/* :492: NaN and negatives never win */
 	    best = Found{ c, a, (unsigned)t, lo, hi };
 	    if (c >= limit)
@@ -564,8 +609,11 @@ __device__ __noinline__ Found find_frame_ws(const Ring rg, unsigned pos_off,
 template <int G, int W, int L>
 __device__ __noinline__ Found find_frame_fast(const Ring rg, unsigned pos_off,
 	const fsk_b200_geom &geo, const LaneWin<W> lw, int sel, unsigned tw_s,
-	unsigned g, unsigned gmask, unsigned try_first, unsigned try_max, unsigned try_step, float limit)
+	unsigned g, unsigned gmask, unsigned try_first, unsigned try_max, unsigned try_step, float limit,
+	int ready = 0, bool pending = false)
 {
+    /* pending: the caller's latest copies into the ring are still in flight, and `ready` samples
+     * from pos_off on are known to have landed; the first candidate waits as late as it can */
     Found best = { 0.f, 0.f, 0u, 0u, 0u };
     for (int j = 0;; j++) {					/* :477-502 */
 	const int up = (j & 1) ? 1 : -1;
@@ -577,7 +625,7 @@ __device__ __noinline__ Found find_frame_fast(const Ring rg, unsigned pos_off,
 	unsigned lo, hi;
 	float a;
 	const float c = frame_analyze_fast<G, W, L>(rg, ring_wrap(pos_off + (unsigned)t, rg.R), geo, lw, sel,
-		tw_s, g, gmask, lo, hi, a);
+		tw_s, g, gmask, lo, hi, a, ready - t, pending);
 	if (best.confidence < c) {			/* NaN and negatives never win */
 	    best = Found{ c, a, (unsigned)t, lo, hi };
 	    if (c >= limit)
@@ -592,9 +640,6 @@ __device__ __noinline__ Found find_frame_fast(const Ring rg, unsigned pos_off,
 /* every sample fetched once; bytes at or past the valid length arrive as 0 */
 /* ------------------------------------------------------------------------ */
 
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int NKEEP>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" :: "n"(NKEEP) : "memory"); }
 
 __device__ __forceinline__ void ldgsts16(unsigned dst, const float *src)
 {

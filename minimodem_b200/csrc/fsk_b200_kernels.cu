@@ -329,13 +329,21 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
 	    const unsigned try_first = carrier ? lc.nsamples_overscan : 0u;	/* :1263 */
 	    const int sel = carrier ? 0 : 1;			/* :1270 data / sync string */
 
+	    int ready = 0;
+	    bool pending = false;
 	    if (MODE == 0) {
 		/* prefetch what the NEXT iteration can need (it starts at most `lookahead`
 		 * samples further), then wait only for what THIS one needs */
 		const unsigned need_now = (pos + try_max - 1u + geo.span + 3u) & ~3u;
 		const bool late = filled < need_now;	/* part of this window is only now requested */
+		ready = (int)(filled - pos);		/* >= -3: what earlier requests cover */
 		request(min((pos + lookahead + need_max + 3u) & ~3u, (pos & ~3u) + R));
-		settle(late);
+		if (FILL == 0) {
+		    /* the search itself waits for the newest copies, after its first stage */
+		    settle(false);
+		    pending = late;
+		} else
+		    settle(late);
 	    }
 	    const GlobalSrc gsrc = { x, n };
 
@@ -344,7 +352,7 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
 	    unsigned frame_start;
 	    if (MODE == 0) {
 		const Found f = find_frame_fast<G, W, L>(rg, pos_off, geo, lw, sel, tw_s, g, gmask,
-			try_first, try_max, try_step, lc.confidence_search_limit);	/* :1265 */
+			try_first, try_max, try_step, lc.confidence_search_limit, ready, pending);	/* :1265 */
 		confidence = f.confidence;
 		amplitude = f.amplitude;
 		frame_start = f.start;
