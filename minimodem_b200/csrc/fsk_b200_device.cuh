@@ -520,22 +520,32 @@ __device__ __forceinline__ float frame_analyze_fast(const Ring rg, unsigned cand
 	    }
 	}
     }
-    /* pass 1 reject, src/fsk.c:211-212 */
-    const bool rejected = WS ? (__ballot_sync(0xffffffffu, mismatch) & gmask_in) != 0u
-			     : __any_sync(gmask, mismatch) != 0;
+    /* pass 1 reject, src/fsk.c:211-212.  The group-masked form does not vote: a lane that saw a
+     * mismatch poisons the noise sum with +inf, and the verdict is read off the reduced sum
+     * (one convergence point fewer per candidate; a noise sum that overflowed by itself would
+     * give confidence 0, which never wins either). */
+    const bool rejected_ws = WS ? (__ballot_sync(0xffffffffu, mismatch) & gmask_in) != 0u : false;
+    if (!WS && mismatch)
+	tn = INFINITY;
+    /* total_sig = sum over marks + sum over spaces; the mark count rides above the bits when
+     * the frame is short enough (disjoint bit positions: OR == ADD) */
+    /* one butterfly for all four: the shuffles share a single convergence guard */
+    unsigned packed = blo | (nm << 24);
+#pragma unroll
+    for (int o = G >> 1; o; o >>= 1) {
+	tn += __shfl_xor_sync(gmask, tn, o);
+	am += __shfl_xor_sync(gmask, am, o);
+	as += __shfl_xor_sync(gmask, as, o);
+	packed += __shfl_xor_sync(gmask, packed, o);
+    }
+    const bool rejected = WS ? rejected_ws : tn == INFINITY;
     if (!WS && rejected) {
 	bits_lo_out = bits_hi_out = 0;
 	ampl_out = 0.f;
 	return 0.f;
     }
-    /* total_sig = sum over marks + sum over spaces; the mark count rides above the bits when
-     * the frame is short enough (disjoint bit positions: OR == ADD) */
-    tn = group_sum<G>(tn, gmask);
-    am = group_sum<G>(am, gmask);
-    as = group_sum<G>(as, gmask);
     const float ts = am + as;
     if (nb <= 24u) {
-	const unsigned packed = group_add<G>(blo | (nm << 24), gmask);
 	blo = packed & 0xffffffu;
 	nm = packed >> 24;
     } else {
@@ -607,7 +617,7 @@ __device__ __noinline__ Found find_frame_ws(const Ring rg, unsigned pos_off,
 
 /* frame search, src/fsk.c:449-538 */
 template <int G, int W, int L>
-__device__ __noinline__ Found find_frame_fast(const Ring rg, unsigned pos_off,
+__device__ __forceinline__ Found find_frame_fast_body(const Ring rg, unsigned pos_off,
 	const fsk_b200_geom &geo, const LaneWin<W> lw, int sel, unsigned tw_s,
 	unsigned g, unsigned gmask, unsigned try_first, unsigned try_max, unsigned try_step, float limit,
 	int ready = 0, bool pending = false)
@@ -633,6 +643,17 @@ __device__ __noinline__ Found find_frame_fast(const Ring rg, unsigned pos_off,
 	}
     }
     return best;
+}
+
+/* the same, as a call: the kernels with more than one search site keep one copy of the code */
+template <int G, int W, int L>
+__device__ __noinline__ Found find_frame_fast(const Ring rg, unsigned pos_off,
+	const fsk_b200_geom &geo, const LaneWin<W> lw, int sel, unsigned tw_s,
+	unsigned g, unsigned gmask, unsigned try_first, unsigned try_max, unsigned try_step, float limit,
+	int ready = 0, bool pending = false)
+{
+    return find_frame_fast_body<G, W, L>(rg, pos_off, geo, lw, sel, tw_s, g, gmask, try_first, try_max,
+	    try_step, limit, ready, pending);
 }
 
 /* ------------------------------------------------------------------------ */

@@ -339,9 +339,14 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
 		ready = (int)(filled - pos);		/* >= -3: what earlier requests cover */
 		request(min((pos + lookahead + need_max + 3u) & ~3u, (pos & ~3u) + R));
 		if (FILL == 0) {
-		    /* the search itself waits for the newest copies, after its first stage */
-		    settle(false);
+#if FSK_STAGE_J < 8
+		    settle(false);	/* two-stage correlation: the first stage needs the older copies */
 		    pending = late;
+#else
+		    /* the search waits for all copies itself, right before its first correlation */
+		    (void)late;
+		    pending = true;
+#endif
 		} else
 		    settle(late);
 	    }
@@ -350,13 +355,41 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
 	    unsigned long long bits;
 	    float amplitude, confidence;
 	    unsigned frame_start;
+	    Found refined = { 0.f, 0.f, 0u, 0u, 0u };
 	    if (MODE == 0) {
-		const Found f = find_frame_fast<G, W, L>(rg, pos_off, geo, lw, sel, tw_s, g, gmask,
-			try_first, try_max, try_step, lc.confidence_search_limit, ready, pending);	/* :1265 */
-		confidence = f.confidence;
-		amplitude = f.amplitude;
-		frame_start = f.start;
-		bits = ((unsigned long long)f.bits_hi << 32) | f.bits_lo;
+		/* one (inlined) search site, taken a second time for the refinement of :1357-1389: whether
+		 * that happens is a pure function of the first result and the loop state, so it is
+		 * decided here and the state machine below only merges the outcome */
+		Found first = { 0.f, 0.f, 0u, 0u, 0u };
+		unsigned step = try_step;
+		float limit = lc.confidence_search_limit;
+		int which = sel;
+		for (int pass = 0;; pass++) {
+		    const Found f = find_frame_fast_body<G, W, L>(rg, pos_off, geo, lw, which, tw_s, g,
+			    gmask, try_first, try_max, step, limit, ready, pending);	/* :1265, :1378 */
+		    if (pass) {
+			refined = f;
+			break;
+		    }
+		    first = f;
+		    float c = f.confidence;
+		    const bool below_peak = c < peak_confidence * 0.75f;	/* :1278 */
+		    if (f.amplitude < track_amplitude * 0.25f)		/* :1286 */
+			c = 0.f;
+		    if (!(c > lc.confidence_threshold) || !(below_peak || !carrier) || !(c < INFINITY)
+			    || try_step <= 1u)
+			break;
+		    step = try_max / 8u;
+		    if (step == 0)
+			step = 1;
+		    limit = INFINITY;
+		    which = 0;
+		    pending = false;
+		}
+		confidence = first.confidence;
+		amplitude = first.amplitude;
+		frame_start = first.start;
+		bits = ((unsigned long long)first.bits_hi << 32) | first.bits_lo;
 	    } else
 		confidence = find_frame<G, GlobalSrc>(gsrc, pos, geo, sel, sm.tw, sm.scr, g, gmask,
 			try_first, try_max, try_step, lc.confidence_search_limit,
@@ -408,12 +441,10 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
 		    unsigned frame_start2;
 		    /* `carrier` is 1 by now, so the data string is searched (:1378) */
 		    if (MODE == 0) {
-			const Found f = find_frame_fast<G, W, L>(rg, pos_off, geo, lw, 0, tw_s, g,
-				gmask, try_first, try_max, try_step, INFINITY);
-			confidence2 = f.confidence;
-			amplitude2 = f.amplitude;
-			frame_start2 = f.start;
-			bits2 = ((unsigned long long)f.bits_hi << 32) | f.bits_lo;
+			confidence2 = refined.confidence;	/* searched above */
+			amplitude2 = refined.amplitude;
+			frame_start2 = refined.start;
+			bits2 = ((unsigned long long)refined.bits_hi << 32) | refined.bits_lo;
 		    } else
 			confidence2 = find_frame<G, GlobalSrc>(gsrc, pos, geo, 0, sm.tw, sm.scr, g,
 				gmask, try_first, try_max, try_step, INFINITY,
