@@ -759,6 +759,24 @@ __device__ __forceinline__ void ring_block(const Ring rg, unsigned ring_s, unsig
     }
 }
 
+/* the same with the lane's addresses carried by the caller: dst/src = this lane's first chunk
+ * of the block, mlim = shared address below which a chunk belongs to the mirrored head */
+template <int G>
+__device__ __forceinline__ void ring_block_at(unsigned dst, const float *__restrict__ src,
+	unsigned mlim, unsigned R)
+{
+    constexpr int CPL = (int)(RING_BLOCK / 4u) / G;
+#pragma unroll
+    for (int k = 0; k < CPL; k++)
+	ldgsts16(dst + (unsigned)k * 16u * G, src + k * 4 * G);
+    if (dst < mlim) {
+#pragma unroll
+	for (int k = 0; k < CPL; k++)
+	    if (dst + (unsigned)k * 16u * G < mlim)
+		ldgsts16(dst + R * 4u + (unsigned)k * 16u * G, src + k * 4 * G);
+    }
+}
+
 /* a block that reaches past the valid length n: bytes at or past n arrive as zeros */
 template <int G>
 __device__ __forceinline__ void ring_block_tail(const Ring rg, unsigned ring_s, unsigned foff,

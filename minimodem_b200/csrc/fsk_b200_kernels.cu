@@ -225,26 +225,27 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
 	bool tail_fix = false;				/* bulk fill: [n, n4) holds row padding, not zeros */
 
 	const unsigned ring_s = rg.ring_s;
-	unsigned foff = 0;				/* block fill: ring offset of `filled` */
+	/* block fill: this lane's running source and destination (its first 16-byte chunk of
+	 * the block that starts at absolute index `filled`), carried instead of recomputed */
+	const unsigned dst0 = ring_s + 16u * g, dst_end = dst0 + R * 4u;
+	const unsigned mlim = ring_s + rg.pad * 4u;	/* chunks below this are mirrored behind the end */
+	unsigned fdst = dst0;
+	const float *fsrc = x + filled + 4u * g;
 	/* request the ring content up to absolute index `to` (rounded up to whole blocks) */
 	auto request = [&](unsigned to) {
 	    if (FILL == 0) {
-		/* whole blocks up to `to`, never past what the ring can hold */
-		const unsigned cap = (pos & ~3u) + R;
-		unsigned nblk = to > filled ? (to - filled + RING_BLOCK - 1u) / RING_BLOCK : 0u;
-		nblk = min(nblk, (cap - filled) / RING_BLOCK);
-		if (filled + nblk * RING_BLOCK <= n) {
-		    for (; nblk; nblk--) {			/* the common case: all of it valid */
-			ring_block<G>(rg, ring_s, foff, x + filled, g);
-			filled += RING_BLOCK;
-			foff = foff + RING_BLOCK == R ? 0u : foff + RING_BLOCK;
-		    }
-		} else {
-		    for (; nblk; nblk--) {			/* end of the stream: zero fill */
-			ring_block_tail<G>(rg, ring_s, foff, x, n, filled, g);
-			filled += RING_BLOCK;
-			foff = foff + RING_BLOCK == R ? 0u : foff + RING_BLOCK;
-		    }
+		/* whole blocks while they start below `to` and still fit in the ring */
+		const unsigned lim = min(to, (pos & ~3u) + R - (RING_BLOCK - 1u));
+		while (filled < lim) {
+		    if (filled + RING_BLOCK <= n)		/* the common case: all of it valid */
+			ring_block_at<G>(fdst, fsrc, mlim, R);
+		    else					/* end of the stream: zero fill */
+			ring_block_tail<G>(rg, ring_s, (fdst - dst0) >> 2, x, n, filled, g);
+		    filled += RING_BLOCK;
+		    fsrc += RING_BLOCK;
+		    fdst += RING_BLOCK * 4u;
+		    if (fdst == dst_end)
+			fdst = dst0;
 		}
 		cp_async_commit();
 	    } else {
@@ -476,7 +477,8 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
 		    drain();
 		    filled = pos & ~3u;
 		    pos_off = pos & 3u;
-		    foff = 0;
+		    fdst = dst0;
+		    fsrc = x + filled + 4u * g;
 		}
 		__syncwarp(gmask);	/* every read of this window precedes the next copies */
 	    }
