@@ -443,7 +443,31 @@ __device__ __forceinline__ float frame_analyze_fast(const Ring rg, unsigned cand
 	pending = false;
     }
     corr_pass<SJ, W, W, L>(acc, p, tw, part, N);
-    if (L > 1) {
+    constexpr int KW = (W + L - 1) / L;
+#ifdef FSK_NO_XCHG
+    constexpr bool XCHG = false;
+#else
+    constexpr bool XCHG = (L == 2);
+#endif
+    /* XCHG (L == 2): instead of an all-reduce that leaves every sum on both lanes of a window, the
+     * two lanes swap the partial sums of the window the OTHER one post-processes (same two
+     * addends, so the same sums): 4 shuffles per round instead of 8 */
+    float ax[KW][4];
+    if (XCHG) {
+#pragma unroll
+	for (int k = 0; k < KW; k++) {
+	    const int j0 = 2 * k, j1 = 2 * k + 1;
+#pragma unroll
+	    for (int c = 0; c < 4; c++) {
+		if (j1 < W) {
+		    const float send = part ? acc[j0][c] : acc[j1][c];
+		    const float mine = part ? acc[j1][c] : acc[j0][c];
+		    ax[k][c] = mine + __shfl_xor_sync(gmask, send, 1);
+		} else
+		    ax[k][c] = acc[j0][c] + __shfl_xor_sync(gmask, acc[j0][c], 1);
+	    }
+	}
+    } else if (L > 1) {
 #pragma unroll
 	for (int o = L >> 1; o; o >>= 1) {
 #pragma unroll
@@ -460,7 +484,6 @@ __device__ __forceinline__ float frame_analyze_fast(const Ring rg, unsigned cand
      * lane part p decides the windows j = p, p+L, ... (KW = ceil(W/L) rounds instead of W).
      * Magnitudes stay unscaled (the 2/N of src/fsk.c:132 is applied once, to the amplitude);
      * the FLT_EPSILON threshold of :279 is scaled the other way instead. */
-    constexpr int KW = (W + L - 1) / L;
     const float eps_u = geo.eps_unscaled;
     float tn = 0.f, am = 0.f, as = 0.f;
     unsigned nm = 0, blo = 0, bhi = 0;
@@ -477,9 +500,14 @@ __device__ __forceinline__ float frame_analyze_fast(const Ring rg, unsigned cand
 	    constexpr int dummy = 0; (void)dummy;
 	    const int j = pp + k * L;
 	    if (j < W && part == (unsigned)pp) {
-		a0 = acc[j][0]; a1 = acc[j][1]; a2 = acc[j][2]; a3 = acc[j][3];
+		if (!XCHG) {
+		    a0 = acc[j][0]; a1 = acc[j][1]; a2 = acc[j][2]; a3 = acc[j][3];
+		}
 		q = p[j];
 	    }
+	}
+	if (XCHG) {
+	    a0 = ax[k][0]; a1 = ax[k][1]; a2 = ax[k][2]; a3 = ax[k][3];
 	}
 	own[k] = (lw.own >> jsel) & 1u;
 	sig[k] = 0.f;
