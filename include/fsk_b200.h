@@ -257,6 +257,48 @@ int fsk_b200_decode_ascii_batch(const fsk_b200_rx_params *p, const fsk_b200_fram
 	const fsk_b200_stream_state *states, size_t nstreams, uint32_t max_frames,
 	uint8_t *out, uint32_t out_stride, uint32_t *out_count, void *stream);
 
+/* N1, all decoders -- the same for any databits decoder of the reference, with the decoder
+ * state the reference keeps in file-static variables (src/baudot.c:197,
+ * src/databits_callerid.c:45-47) held per stream. */
+#define FSK_B200_DECODE_ASCII		0	/* databits_decode_ascii8, src/databits_ascii.c:35-44 */
+#define FSK_B200_DECODE_BINARY		1	/* databits_decode_binary, src/databits_binary.c:29-41 */
+#define FSK_B200_DECODE_BAUDOT		2	/* databits_decode_baudot, src/databits_baudot.c:30-40 */
+#define FSK_B200_DECODE_CALLERID	3	/* databits_decode_callerid, src/databits_callerid.c:163-209 */
+#define FSK_B200_DECODE_UIC_GROUND	4	/* databits_decode_uic_ground, src/databits_uic.c:54-63 */
+#define FSK_B200_DECODE_UIC_TRAIN	5	/* databits_decode_uic_train, src/databits_uic.c:65-74 */
+
+typedef struct fsk_b200_decoder_state {
+    uint32_t	baudot_charset;		/* src/baudot.c:197: 0 unknown, 1 LTRS, 2 FIGS */
+    uint32_t	cid_msgtype;		/* src/databits_callerid.c:45 */
+    uint32_t	cid_ndata;		/* :46 */
+    uint32_t	reserved;
+    uint8_t	cid_buf[256];		/* :47; never cleared between messages, as there */
+} fsk_b200_decoder_state;		/* 272 bytes; all zeros = the reference at program start */
+
+/* Which decoder the reference's main() would pick (src/minimodem.c:552, :675, :820, :828, :856,
+ * :866-868, :891-892): baudmode as given to fsk_b200_rx_config_for_mode, n_data_bits == 5 stands
+ * for the -5/--baudot option, binary_output for the --binary-output / --binary-raw switches. */
+int fsk_b200_decoder_for_mode(const char *baudmode, unsigned int n_data_bits, int binary_output);
+
+/* Most bytes one frame record can become under `kind` (Caller-ID prints a whole message on
+ * its last byte), and most bytes `nframes` records of one stream can become -- the out_stride
+ * that never truncates (Caller-ID: a message of L bytes takes L+2 records, so the bound is an
+ * amortised 141 bytes per record plus one message carried in from an earlier batch). */
+uint32_t fsk_b200_decode_max_bytes_per_frame(int kind, unsigned int n_data_bits);
+uint64_t fsk_b200_decode_max_bytes(int kind, unsigned int n_data_bits, uint32_t nframes);
+
+/* For every stream, the records [0, states[s].nframes) of frames[s*max_frames ...] go through
+ * the rx loop's chop (src/minimodem.c:1415-1439), the decoder reset on the record that
+ * acquired the carrier (:1351) and decoder `kind`; bytes land in out[s*out_stride ...],
+ * out_count[s] = bytes produced, at most out_stride (the excess is dropped).  dstates: one
+ * fsk_b200_decoder_state per stream, read and written back, so that a stream decoded in
+ * several batches continues where it stopped; NULL = start every stream from zeros.
+ * All pointers are device memory. */
+int fsk_b200_decode_batch(const fsk_b200_rx_params *p, int kind, const fsk_b200_frame *frames,
+	const fsk_b200_stream_state *states, size_t nstreams, uint32_t max_frames,
+	fsk_b200_decoder_state *dstates,
+	uint8_t *out, uint32_t out_stride, uint32_t *out_count, void *stream);
+
 /* Upper bound on frame records a stream of nsamples can produce. */
 uint32_t fsk_b200_max_frames(const fsk_b200_rx_params *p, uint32_t nsamples);
 

@@ -100,6 +100,8 @@ EXPORTS = [
     "fsk_b200_find_frame_batch", "fsk_b200_rx_batch", "fsk_b200_rx_batch_host",
     "fsk_b200_max_frames", "fsk_b200_frame_databits", "fsk_b200_tx_batch", "fsk_b200_sin_table",
     "fsk_b200_s16_to_f32", "fsk_b200_rx_batch_host_s16", "fsk_b200_decode_ascii_batch",
+    "fsk_b200_decode_batch", "fsk_b200_decoder_for_mode", "fsk_b200_decode_max_bytes_per_frame",
+    "fsk_b200_decode_max_bytes",
     "fsk_b200_version", "fsk_b200_launch_count", "fsk_b200_last_error",
 ]
 
@@ -172,6 +174,16 @@ def lib():
     L.fsk_b200_decode_ascii_batch.argtypes = [C.POINTER(RxParams), C.c_void_p, C.c_void_p, C.c_size_t,
                                               C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
     L.fsk_b200_decode_ascii_batch.restype = C.c_int
+    L.fsk_b200_decode_batch.argtypes = [C.POINTER(RxParams), C.c_int, C.c_void_p, C.c_void_p, C.c_size_t,
+                                        C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
+                                        C.c_void_p]
+    L.fsk_b200_decode_batch.restype = C.c_int
+    L.fsk_b200_decoder_for_mode.argtypes = [C.c_char_p, C.c_uint, C.c_int]
+    L.fsk_b200_decoder_for_mode.restype = C.c_int
+    L.fsk_b200_decode_max_bytes_per_frame.argtypes = [C.c_int, C.c_uint]
+    L.fsk_b200_decode_max_bytes_per_frame.restype = C.c_uint32
+    L.fsk_b200_decode_max_bytes.argtypes = [C.c_int, C.c_uint, C.c_uint32]
+    L.fsk_b200_decode_max_bytes.restype = C.c_uint64
     L.fsk_b200_sin_table.argtypes = [C.POINTER(C.c_float), C.c_uint, C.c_float]
     L.fsk_b200_sin_table.restype = None
     L.fsk_b200_version.restype = C.c_char_p
@@ -416,6 +428,27 @@ class RxEngine:
             _err("fsk_b200_decode_ascii_batch", rc)
         return out, cnt
 
+    def decode_batch(self, kind, frames, states, dstates=None, out_stride=None, stream=None):
+        """Device-side databits decode (N1) of the records of rx_batch with decoder `kind`
+        (DECODE_*): CUDA tensors in, (bytes [nstreams, out_stride] uint8, counts [nstreams] int32)
+        out.  dstates: uint8 CUDA tensor [nstreams, DECODER_STATE_BYTES] carrying each stream's
+        decoder state from batch to batch (updated in place), or None to start from zeros."""
+        torch = _torch()
+        nstreams, max_frames = frames.shape[0], frames.shape[1]
+        if out_stride is None:
+            out_stride = decode_max_bytes(kind, self.params.n_data_bits, max_frames)
+        out_stride = int(out_stride)
+        out = torch.zeros((nstreams, out_stride), dtype=torch.uint8, device=frames.device)
+        cnt = torch.zeros((nstreams,), dtype=torch.int32, device=frames.device)
+        if dstates is not None:
+            assert dstates.dtype == torch.uint8 and tuple(dstates.shape) == (nstreams, DECODER_STATE_BYTES)
+        rc = lib().fsk_b200_decode_batch(C.byref(self.params), int(kind), _ptr(frames), _ptr(states), nstreams,
+                                         max_frames, _ptr(dstates) if dstates is not None else None,
+                                         _ptr(out), out_stride, _ptr(cnt), _stream_handle(stream))
+        if rc:
+            _err("fsk_b200_decode_batch", rc)
+        return out, cnt
+
     def destroy(self):
         if self._e:
             lib().fsk_b200_engine_destroy(self._e)
@@ -426,6 +459,34 @@ class RxEngine:
             self.destroy()
         except Exception:
             pass
+
+
+# N1 decoders (include/fsk_b200.h FSK_B200_DECODE_*)
+DECODE_ASCII, DECODE_BINARY, DECODE_BAUDOT, DECODE_CALLERID, DECODE_UIC_GROUND, DECODE_UIC_TRAIN = range(6)
+DECODER_STATE_BYTES = 272
+
+
+class DecoderState(C.Structure):
+    """fsk_b200_decoder_state"""
+    _fields_ = [("baudot_charset", C.c_uint32), ("cid_msgtype", C.c_uint32), ("cid_ndata", C.c_uint32),
+                ("reserved", C.c_uint32), ("cid_buf", C.c_uint8 * 256)]
+
+
+def decoder_for_mode(baudmode, n_data_bits=8, binary_output=False):
+    """Which decoder the reference's main() would use (src/minimodem.c:552-892)."""
+    k = lib().fsk_b200_decoder_for_mode(str(baudmode).encode(), int(n_data_bits), int(bool(binary_output)))
+    if k < 0:
+        _err("fsk_b200_decoder_for_mode", k)
+    return k
+
+
+def decode_max_bytes_per_frame(kind, n_data_bits):
+    return int(lib().fsk_b200_decode_max_bytes_per_frame(int(kind), int(n_data_bits)))
+
+
+def decode_max_bytes(kind, n_data_bits, nframes):
+    """out_stride that never truncates `nframes` records of one stream."""
+    return int(lib().fsk_b200_decode_max_bytes(int(kind), int(n_data_bits), int(nframes)))
 
 
 def frames_to_numpy(frames):

@@ -258,8 +258,11 @@ int fsk_b200_rx_params_derive(const fsk_b200_rx_config *cfg, fsk_b200_rx_params 
     p->frame_nsamples = p->nsamples_per_bit * frame_n_bits + 0.5f;	/* :1113 */
 
     if (cfg->expect_data_string[0]) {				/* :1116 (uic supplies one) */
-	strncpy(p->expect_data, cfg->expect_data_string, FSK_B200_MAX_BITS);
-	p->expect_n_bits = strlen(p->expect_data);
+	/* at most FSK_B200_MAX_BITS characters (the reference asserts that in src/fsk.c:463) */
+	size_t n = strnlen(cfg->expect_data_string, FSK_B200_MAX_BITS);
+	memcpy(p->expect_data, cfg->expect_data_string, n);
+	p->expect_data[n] = 0;
+	p->expect_n_bits = (unsigned int)n;
     } else {
 	p->expect_n_bits = build_expect(p->expect_data, cfg->nstartbits, cfg->n_data_bits,
 		cfg->nstopbits, cfg->invert_start_stop, 0, 0);
@@ -481,18 +484,79 @@ int fsk_b200_rx_batch_host_s16(fsk_b200_engine *e, const int16_t *host_samples, 
 	    stride, nsamples_all, host_frames, max_frames, host_states);
 }
 
-int fsk_b200_decode_ascii_batch(const fsk_b200_rx_params *p, const fsk_b200_frame *frames,
+int fsk_b200_decoder_for_mode(const char *baudmode, unsigned int n_data_bits, int binary_output)
+{
+    int kind = FSK_B200_DECODE_ASCII;				/* src/minimodem.c:552 */
+    if (!baudmode)
+	return -EINVAL;
+    if (n_data_bits == 5)					/* -5/--baudot, :673-676 */
+	kind = FSK_B200_DECODE_BAUDOT;
+    if (strncasecmp(baudmode, "rtty", 5) == 0 || strncasecmp(baudmode, "tdd", 4) == 0)
+	kind = FSK_B200_DECODE_BAUDOT;				/* :820, :828 */
+    else if (strncasecmp(baudmode, "caller", 6) == 0)
+	kind = FSK_B200_DECODE_CALLERID;			/* :856 */
+    else if (strncasecmp(baudmode, "uic", 3) == 0)		/* :865-868: "uic-t..." is train-to-ground */
+	kind = strlen(baudmode) > 4 && tolower((unsigned char)baudmode[4]) == 't'
+		? FSK_B200_DECODE_UIC_TRAIN : FSK_B200_DECODE_UIC_GROUND;
+    if (binary_output)
+	kind = FSK_B200_DECODE_BINARY;				/* :891-892 */
+    return kind;
+}
+
+uint32_t fsk_b200_decode_max_bytes_per_frame(int kind, unsigned int n_data_bits)
+{
+    switch (kind) {
+	case FSK_B200_DECODE_ASCII:
+	case FSK_B200_DECODE_BAUDOT:
+	    return 1;
+	case FSK_B200_DECODE_BINARY:
+	    return n_data_bits + 1;
+	case FSK_B200_DECODE_CALLERID:
+	    /* "CALLER-ID\n" + at most 127 two-byte fields of 10 label bytes, or one 255-byte field */
+	    return 10 + 127 * 10 + 256;
+	case FSK_B200_DECODE_UIC_GROUND:
+	case FSK_B200_DECODE_UIC_TRAIN:
+	    /* "Train ID: XXXXXX - Message: XX (" + the longest meaning (25) + ")\n" */
+	    return 32 + 25 + 2;
+	default:
+	    return 0;
+    }
+}
+
+uint64_t fsk_b200_decode_max_bytes(int kind, unsigned int n_data_bits, uint32_t nframes)
+{
+    if (kind == FSK_B200_DECODE_CALLERID)
+	/* SDMF with a wrapped length is the densest: "CALLER-ID\n" + two labels + a date + up to
+	 * 246 buffer bytes + '\n' = 282 bytes for 2 records */
+	return (uint64_t)141 * nframes + fsk_b200_decode_max_bytes_per_frame(kind, n_data_bits);
+    return (uint64_t)fsk_b200_decode_max_bytes_per_frame(kind, n_data_bits) * nframes;
+}
+
+int fsk_b200_decode_batch(const fsk_b200_rx_params *p, int kind, const fsk_b200_frame *frames,
 	const fsk_b200_stream_state *states, size_t nstreams, uint32_t max_frames,
+	fsk_b200_decoder_state *dstates,
 	uint8_t *out, uint32_t out_stride, uint32_t *out_count, void *stream)
 {
     if (!p || !frames || !states || !out || !out_count || out_stride == 0 || max_frames == 0) {
-	fsk_b200_set_error("decode_ascii_batch: NULL argument");
+	fsk_b200_set_error("decode_batch: NULL argument");
+	return -EINVAL;
+    }
+    if (kind < FSK_B200_DECODE_ASCII || kind > FSK_B200_DECODE_UIC_TRAIN) {
+	fsk_b200_set_error("decode_batch: unknown decoder %d", kind);
 	return -EINVAL;
     }
     /* src/minimodem.c:1415 (drop the previous stop bit) + bit_window's offset */
     unsigned shift = (p->nstopbits != 0.0f ? 1u : 0u) + (unsigned)p->nstartbits;
-    return fsk_b200_cuda_decode_ascii(shift, p->n_data_bits, p->msb_first, p->do_rx_sync, p->sync_byte,
-	    frames, states, nstreams, max_frames, out, out_stride, out_count, stream);
+    return fsk_b200_cuda_decode(kind, shift, p->n_data_bits, p->msb_first, p->do_rx_sync, p->sync_byte,
+	    frames, states, nstreams, max_frames, dstates, out, out_stride, out_count, stream);
+}
+
+int fsk_b200_decode_ascii_batch(const fsk_b200_rx_params *p, const fsk_b200_frame *frames,
+	const fsk_b200_stream_state *states, size_t nstreams, uint32_t max_frames,
+	uint8_t *out, uint32_t out_stride, uint32_t *out_count, void *stream)
+{
+    return fsk_b200_decode_batch(p, FSK_B200_DECODE_ASCII, frames, states, nstreams, max_frames, NULL,
+	    out, out_stride, out_count, stream);
 }
 
 void fsk_b200_sin_table(float *out, unsigned int len, float mag)

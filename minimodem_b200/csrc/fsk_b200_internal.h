@@ -71,10 +71,10 @@ int  fsk_b200_cuda_s16_to_f32(const int16_t *src, float *dst, size_t nstreams, s
 int  fsk_b200_cuda_rx_batch_host_s16(void *ce, const fsk_b200_geom *g, const fsk_b200_loopc *lc,
 	const int16_t *host_samples, size_t nstreams, size_t stride, uint32_t nsamples_all,
 	fsk_b200_frame *host_frames, uint32_t max_frames, fsk_b200_stream_state *host_states);
-int  fsk_b200_cuda_decode_ascii(unsigned shift, unsigned n_data_bits, int msb_first, int do_rx_sync,
+int  fsk_b200_cuda_decode(int kind, unsigned shift, unsigned n_data_bits, int msb_first, int do_rx_sync,
 	unsigned long long sync_byte, const fsk_b200_frame *frames, const fsk_b200_stream_state *states,
-	size_t nstreams, uint32_t max_frames, uint8_t *out, uint32_t out_stride, uint32_t *out_count,
-	void *stream);
+	size_t nstreams, uint32_t max_frames, fsk_b200_decoder_state *dstates, uint8_t *out,
+	uint32_t out_stride, uint32_t *out_count, void *stream);
 unsigned long long fsk_b200_cuda_launch_count(void);
 
 #ifdef __cplusplus

@@ -22,7 +22,7 @@
  * k_rx<G,W,L,MODE,FILL>   the whole rx loop per stream (MODE 0 fast / 1 generic)
  * k_rx_ws<G,W,L>          the same, warp-synchronous (selectable, measured slower)
  * k_find_frame<G,W,L,MODE> batched fsk_find_frame
- * k_tx, k_band_mags, k_s16_to_f32, k_decode_ascii   the "next" rows
+ * k_tx, k_band_mags, k_s16_to_f32, k_decode<KIND>   the "next" rows
  *
  * Compiled with -fmad=false: every a*b+c below is either an explicit fmaf() (the
  * correlation sums) or two separately rounded operations, as in the reference's
@@ -40,6 +40,7 @@
 
 #include "fsk_b200_internal.h"
 #include "fsk_b200_device.cuh"
+#include "fsk_b200_decode_core.h"
 
 static unsigned long long g_launches;
 
@@ -870,12 +871,15 @@ __global__ void k_s16_to_f32_scalar(const short *__restrict__ src, float *__rest
 }
 
 /* ------------------------------------------------------------------------ */
-/* N1: frame records -> bytes, databits_decode_ascii8 (src/databits_ascii.c:35-44)
- * behind the bit chop of src/minimodem.c:1415-1446; one thread per stream    */
+/* N1: frame records -> bytes through one of the reference's databits decoders  */
+/* (fsk_b200_decode_core.h) behind the bit chop of src/minimodem.c:1415-1446;   */
+/* one thread per stream, the decoder state of the stream in registers/local    */
 /* ------------------------------------------------------------------------ */
-__global__ void k_decode_ascii(unsigned shift, unsigned n_data_bits, int msb_first, int do_rx_sync,
+template <int KIND>
+__global__ void k_decode(unsigned shift, unsigned n_data_bits, int msb_first, int do_rx_sync,
 	unsigned long long sync_byte, const fsk_b200_frame *__restrict__ frames,
 	const fsk_b200_stream_state *__restrict__ states, unsigned nstreams, uint32_t max_frames,
+	fsk_b200_decoder_state *__restrict__ dstates,
 	uint8_t *__restrict__ out, uint32_t out_stride, uint32_t *__restrict__ out_count)
 {
     const unsigned s = blockIdx.x * blockDim.x + threadIdx.x;
@@ -883,27 +887,24 @@ __global__ void k_decode_ascii(unsigned shift, unsigned n_data_bits, int msb_fir
 	return;
     const unsigned nrec = min(states[s].nframes, max_frames);
     const uint32_t *rec = reinterpret_cast<const uint32_t *>(frames + (size_t)s * max_frames);
-    uint8_t *o = out + (size_t)s * out_stride;
-    unsigned k = 0;
-    const unsigned long long mask = n_data_bits < 64 ? (1ull << n_data_bits) - 1ull : ~0ull;
-    for (unsigned i = 0; i < nrec; i++, rec += 5) {
-	if (rec[4] == FSK_B200_FRAME_REPORT)
-	    continue;				/* a carrier-session report, not a frame */
-	unsigned long long bits = ((unsigned long long)rec[1] << 32) | rec[0];
-	bits = (bits >> shift) & mask;		/* :1415 chop + bit_window (src/databits.h:35-46) */
-	if (msb_first) {			/* bit_reverse keeps 32 bits (src/databits.h:21-33) */
-	    unsigned r = 0;
-	    for (unsigned b = 0; b < n_data_bits; b++)
-		r = (r << 1) | (unsigned)((bits >> b) & 1ull);
-	    bits = r;
-	}
-	if (do_rx_sync && bits == sync_byte)	/* :1436-1439 */
-	    continue;
-	if (k < out_stride)
-	    o[k] = (uint8_t)(bits & 0xff);	/* databits_decode_ascii8 */
-	k++;
-    }
-    out_count[s] = min(k, out_stride);
+    fsk_dec_sink sink = { out + (size_t)s * out_stride, out_stride, 0u };
+    /* Caller-ID collects into the stream's own state block in global memory (256 bytes per
+     * stream do not belong in registers); the others carry a few words */
+    fsk_b200_decoder_state local;
+    fsk_b200_decoder_state *st = &local;
+    if (KIND == FSK_B200_DECODE_CALLERID && dstates)
+	st = dstates + s;
+    else if (KIND == FSK_B200_DECODE_CALLERID) {
+	local.cid_msgtype = local.cid_ndata = 0;
+	for (int i = 0; i < 256; i++)
+	    local.cid_buf[i] = 0;
+    } else
+	local.baudot_charset = dstates ? dstates[s].baudot_charset : 0u;
+    for (unsigned i = 0; i < nrec; i++, rec += 5)
+	fsk_dec_record(KIND, shift, n_data_bits, msb_first, do_rx_sync, sync_byte, st, rec, &sink);
+    if (KIND == FSK_B200_DECODE_BAUDOT && dstates)
+	dstates[s].baudot_charset = local.baudot_charset;
+    out_count[s] = min(sink.n, out_stride);
 }
 
 /* ======================================================================== */
@@ -1443,20 +1444,35 @@ extern "C" int fsk_b200_cuda_s16_to_f32(const int16_t *src, float *dst, size_t n
     return 0;
 }
 
-extern "C" int fsk_b200_cuda_decode_ascii(unsigned shift, unsigned n_data_bits, int msb_first,
+extern "C" int fsk_b200_cuda_decode(int kind, unsigned shift, unsigned n_data_bits, int msb_first,
 	int do_rx_sync, unsigned long long sync_byte, const fsk_b200_frame *frames,
-	const fsk_b200_stream_state *states, size_t nstreams, uint32_t max_frames, uint8_t *out,
-	uint32_t out_stride, uint32_t *out_count, void *stream)
+	const fsk_b200_stream_state *states, size_t nstreams, uint32_t max_frames,
+	fsk_b200_decoder_state *dstates, uint8_t *out, uint32_t out_stride, uint32_t *out_count,
+	void *stream)
 {
     if (nstreams == 0)
 	return 0;
-    k_decode_ascii<<<(unsigned)((nstreams + 127) / 128), 128, 0, (cudaStream_t)stream>>>(shift,
-	    n_data_bits, msb_first, do_rx_sync, sync_byte, frames, states, (unsigned)nstreams,
-	    max_frames, out, out_stride, out_count);
+    const unsigned blocks = (unsigned)((nstreams + 127) / 128);
+    cudaStream_t st = (cudaStream_t)stream;
+#define DECODE_CASE(K) case K: k_decode<K><<<blocks, 128, 0, st>>>(shift, n_data_bits, msb_first, \
+	    do_rx_sync, sync_byte, frames, states, (unsigned)nstreams, max_frames, dstates, out, \
+	    out_stride, out_count); break
+    switch (kind) {
+	DECODE_CASE(FSK_B200_DECODE_ASCII);
+	DECODE_CASE(FSK_B200_DECODE_BINARY);
+	DECODE_CASE(FSK_B200_DECODE_BAUDOT);
+	DECODE_CASE(FSK_B200_DECODE_CALLERID);
+	DECODE_CASE(FSK_B200_DECODE_UIC_GROUND);
+	DECODE_CASE(FSK_B200_DECODE_UIC_TRAIN);
+	default:
+	    fsk_b200_set_error("decode: unknown decoder %d", kind);
+	    return -EINVAL;
+    }
+#undef DECODE_CASE
     g_launches++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
-	fsk_b200_set_error("decode_ascii launch: %s", cudaGetErrorString(e));
+	fsk_b200_set_error("decode launch: %s", cudaGetErrorString(e));
 	return -EIO;
     }
     return 0;

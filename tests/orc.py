@@ -136,6 +136,12 @@ def lib():
         L.orc_rx_result_free.argtypes = [C.POINTER(OrcRxResult)]
         L.orc_rx_databits.argtypes = [C.POINTER(OrcRxConfig), C.c_ulonglong]
         L.orc_rx_databits.restype = C.c_ulonglong
+        L.orc_decode_words.argtypes = [C.c_int, C.c_uint, C.c_void_p, C.POINTER(C.c_ulonglong), C.c_uint,
+                                       C.c_char_p, C.c_char_p, C.c_uint]
+        L.orc_decode_words.restype = C.c_uint
+        L.orc_decode_records.argtypes = [C.c_int, C.c_uint, C.c_uint, C.c_int, C.c_int, C.c_ulonglong,
+                                         C.c_void_p, C.c_void_p, C.c_uint, C.c_char_p, C.c_uint]
+        L.orc_decode_records.restype = C.c_uint
         L.orc_rx_many.argtypes = [C.POINTER(OrcRxConfig), fp, C.c_size_t, C.c_size_t, C.c_size_t,
                                   C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.POINTER(C.c_uint), C.POINTER(C.c_ulonglong)]
@@ -393,6 +399,57 @@ def tx_words(mode, words, amplitude=1.0, lut=4096, float_samples=False):
 def databits(mode, bits):
     cfg = mode.rx_config()
     return lib().orc_rx_databits(C.byref(cfg), bits)
+
+
+# ---- N1: the host build of the product's decoder source (oracle/decode_oracle.c) ------------
+DECODE_KINDS = {"ascii8": 0, "binary": 1, "baudot": 2, "callerid": 3, "uic-ground": 4, "uic-train": 5}
+FRAME_ACQUIRED = 0x80000000
+FRAME_REPORT = 0xFFFFFFFF
+
+
+class DecoderState(C.Structure):
+    """fsk_b200_decoder_state (include/fsk_b200.h)"""
+    _fields_ = [("baudot_charset", C.c_uint32), ("cid_msgtype", C.c_uint32), ("cid_ndata", C.c_uint32),
+                ("reserved", C.c_uint32), ("cid_buf", C.c_uint8 * 256)]
+
+
+def decode_words(kind, n_data_bits, words, resets=None, state=None, cap=1 << 20):
+    """data words -> bytes through decoder `kind` (name or number); resets[i] = a decoder reset
+    before word i.  `state` (DecoderState) persists across calls when given."""
+    k = DECODE_KINDS.get(kind, kind)
+    st = state if state is not None else DecoderState()
+    w = (C.c_ulonglong * max(len(words), 1))(*[int(x) for x in words])
+    rb = bytes(1 if r else 0 for r in resets) if resets is not None else None
+    buf = C.create_string_buffer(cap)
+    n = lib().orc_decode_words(k, n_data_bits, C.addressof(st), w, len(words), rb, buf, cap)
+    return buf.raw[:min(n, cap)]
+
+
+def frame_records(frames, reports_at=None):
+    """oracle frames [(bits, conf, ampl, start, acquired, pos)...] -> uint32 [n, 5] records as
+    rx_batch writes them (include/fsk_b200.h fsk_b200_frame)."""
+    rec = np.zeros((len(frames), 5), np.uint32)
+    for i, fr in enumerate(frames):
+        rec[i, 0] = fr[0] & 0xFFFFFFFF
+        rec[i, 1] = fr[0] >> 32
+        rec[i, 2] = np.float32(fr[1]).view(np.uint32)
+        rec[i, 3] = np.float32(fr[2]).view(np.uint32)
+        rec[i, 4] = fr[3] | (FRAME_ACQUIRED if fr[4] else 0)
+    return rec
+
+
+def decode_records(mode, kind, records, state=None, cap=1 << 20):
+    """uint32 [n, 5] frame records -> bytes, the walk k_decode does per stream."""
+    k = DECODE_KINDS.get(kind, kind)
+    st = state if state is not None else DecoderState()
+    rec = np.ascontiguousarray(records, np.uint32).reshape(-1, 5)
+    shift = (1 if mode.nstopbits != 0.0 else 0) + int(mode.nstartbits)
+    sync = mode.sync_byte if mode.sync_byte is not None else 0xFFFFFFFFFFFFFFFF
+    buf = C.create_string_buffer(cap)
+    n = lib().orc_decode_records(k, shift, mode.n_data_bits, int(mode.msb_first), int(mode.do_rx_sync),
+                                 sync & 0xFFFFFFFFFFFFFFFF, C.addressof(st), rec.ctypes.data, rec.shape[0],
+                                 buf, cap)
+    return buf.raw[:min(n, cap)]
 
 
 def report_line(mode, report):

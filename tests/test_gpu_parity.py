@@ -533,3 +533,128 @@ def test_s16_ingest_and_device_ascii_decode(name):
     want = bytes(g["stdout"])
     for s in range(nstreams):
         assert bytes(o[s, :c[s]]) == want, s
+
+
+# --------------------------------------------------------------------------
+# N1: every databits decoder on the device (k_decode<KIND>) against the host build of the
+# same source (oracle/decode_oracle.c), which test_decoders.py pins to the reference decoders
+# --------------------------------------------------------------------------
+DEC_MODES = {"ascii8": ("1200", {}), "binary": ("1200", {}), "baudot": ("rtty", dict(sample_rate=8000)),
+             "callerid": ("callerid", {}), "uic-ground": ("uic-ground", {}), "uic-train": ("uic-train", {})}
+
+
+def _synthetic_records(kind, rx, rng, nstreams, max_frames):
+    """Frame records a demodulator could have written: data words under the mode's framing, a
+    carrier acquire here and there, session reports in between, ragged record counts."""
+    nb = rx.n_data_bits
+    shift = (1 if rx.nstopbits != 0.0 else 0) + int(rx.nstartbits)
+    rec = np.zeros((nstreams, max_frames, 5), np.uint32)
+    nfr = rng.integers(0, max_frames + 1, nstreams).astype(np.uint32)
+    nfr[:4] = [0, 1, max_frames, max_frames]
+    for s in range(nstreams):
+        n = int(nfr[s])
+        if kind == "callerid":
+            # byte traffic with frequent message starts and short lengths, so that messages complete
+            w = rng.integers(0, 256, n, dtype=np.uint64)
+            i = 0
+            while i + 2 < n:
+                ln = int(rng.integers(0, 24))
+                w[i] = int(rng.choice([0x80, 0x04]))
+                w[i + 1] = ln
+                if w[i] == 0x80:
+                    j = i + 2
+                    while j + 2 <= min(n, i + 2 + ln):
+                        w[j] = int(rng.choice([1, 2, 4, 7, 8, 3, 9]))
+                        fl = int(min(rng.integers(0, 11), i + 2 + ln - j - 2))
+                        w[j + 1] = fl
+                        j += 2 + fl
+                i += ln + 3 + int(rng.integers(0, 3))
+        elif kind == "baudot":
+            w = rng.integers(0, 32, n, dtype=np.uint64)
+        else:
+            w = rng.integers(0, 1 << min(nb, 62), n, dtype=np.uint64)
+        junk = rng.integers(0, 1 << 62, n, dtype=np.uint64)
+        mask = np.uint64(((1 << nb) - 1) << shift)
+        bits = ((w << np.uint64(shift)) & mask) | (junk & ~mask)       # framing bits are arbitrary
+        if rx.frame_n_bits + 1 < 64:
+            bits &= np.uint64((1 << (rx.frame_n_bits + 1)) - 1)
+        rec[s, :n, 0] = (bits & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+        rec[s, :n, 1] = (bits >> np.uint64(32)).astype(np.uint32)
+        rec[s, :n, 4] = rng.integers(0, 100, n).astype(np.uint32)
+        acq = rng.random(n) < 0.03
+        if n:
+            acq[0] = True
+        rec[s, :n, 4] |= np.where(acq, orc.FRAME_ACQUIRED, 0).astype(np.uint32)
+        rep = rng.random(n) < 0.02
+        rec[s, :n, 4] = np.where(rep, orc.FRAME_REPORT, rec[s, :n, 4])
+    return rec, nfr
+
+
+@pytest.mark.parametrize("kind", list(DEC_MODES))
+def test_decode_batch_every_decoder(kind):
+    mode, kw = DEC_MODES[kind]
+    rx = orc.Mode(mode, **kw)
+    eng, _ = engine_for((mode, kw))
+    k = orc.DECODE_KINDS[kind]
+    assert mm.decoder_for_mode(mode, rx.n_data_bits, binary_output=(kind == "binary")) == k
+    rng = np.random.default_rng(100 + k)
+    nstreams, max_frames = 700, 96
+    rec, nfr = _synthetic_records(kind, rx, rng, nstreams, max_frames)
+    st = np.zeros(nstreams, mm.STATE_DTYPE)
+    st["nframes"] = nfr
+    d_rec = torch.from_numpy(rec.view(np.int32)).to(dev())
+    d_st = torch.from_numpy(st.view(np.int32).reshape(nstreams, -1)).to(dev())
+    out, cnt = eng.decode_batch(k, d_rec, d_st)
+    torch.cuda.synchronize()
+    o, c = out.cpu().numpy(), cnt.cpu().numpy()
+    total = 0
+    for s in range(nstreams):
+        want = orc.decode_records(rx, kind, rec[s, :nfr[s]])
+        assert bytes(o[s, :c[s]]) == want, (kind, s)
+        total += len(want)
+    assert total > 1000
+
+    # the same streams in two batches with the decoder state carried on the device
+    half = max_frames // 2
+    dst = torch.zeros((nstreams, mm.DECODER_STATE_BYTES), dtype=torch.uint8, device=dev())
+    st1 = st.copy()
+    st1["nframes"] = np.minimum(nfr, half)
+    st2 = st.copy()
+    st2["nframes"] = nfr - st1["nframes"]
+    rec2 = np.zeros_like(rec)
+    rec2[:, :max_frames - half] = rec[:, half:]
+    o1, c1 = eng.decode_batch(k, d_rec, torch.from_numpy(st1.view(np.int32).reshape(nstreams, -1)).to(dev()), dstates=dst)
+    o2, c2 = eng.decode_batch(k, torch.from_numpy(rec2.view(np.int32)).to(dev()),
+                              torch.from_numpy(st2.view(np.int32).reshape(nstreams, -1)).to(dev()), dstates=dst)
+    torch.cuda.synchronize()
+    o1, c1, o2, c2 = o1.cpu().numpy(), c1.cpu().numpy(), o2.cpu().numpy(), c2.cpu().numpy()
+    for s in range(nstreams):
+        assert bytes(o1[s, :c1[s]]) + bytes(o2[s, :c2[s]]) == bytes(o[s, :c[s]]), (kind, s)
+
+    # a short output row: the count is clamped, the stored prefix is intact
+    o3, c3 = eng.decode_batch(k, d_rec, d_st, out_stride=7)
+    torch.cuda.synchronize()
+    o3, c3 = o3.cpu().numpy(), c3.cpu().numpy()
+    for s in range(0, nstreams, 37):
+        assert c3[s] == min(c[s], 7) and bytes(o3[s, :c3[s]]) == bytes(o[s, :c3[s]])
+
+
+@pytest.mark.parametrize("name", ["03-self-test-rtty", "81-tdd", "70-callerid-mdmf", "71-callerid-sdmf", "small-rtty"])
+def test_rx_then_device_decode_prints_what_the_reference_printed(name):
+    """Samples in, text out, all on the device: rx_batch + decode_batch with the decoder the
+    reference's main() picks for the mode = the stdout of the unmodified reference CLI."""
+    case = refcases.BY_NAME[name]
+    g = gu.load(name)
+    _, rx = gu.modes(case)
+    a = gu.audio(case, g)
+    eng, cfg = engine_for(case)
+    n = a.size
+    buf = np.zeros((2, pad4(n)), np.float32)
+    buf[:, :n] = a
+    frames, states = eng.rx_batch(torch.from_numpy(buf).to(dev()), nsamples=n)
+    kind = mm.decoder_for_mode(case["rx_mode"], rx.n_data_bits)
+    out, cnt = eng.decode_batch(kind, frames, states)
+    torch.cuda.synchronize()
+    o, c = out.cpu().numpy(), cnt.cpu().numpy()
+    for s in range(2):
+        assert bytes(o[s, :c[s]]) == bytes(g["stdout"]), s
