@@ -90,4 +90,38 @@ SMALL = [
 ]
 
 ALL = CASES + SMALL
-BY_NAME = {c["name"]: c for c in ALL}
+
+# Option combinations none of the reference's own tests use (framing, bit order, tone
+# inversion, sync byte, odd sample rates, thresholds): short payloads, audio committed.
+# Minted like the others from the unmodified reference CLI.  They pin the oracle (CPU tests);
+# the GPU list (tests/test_gpu_parity.py RX_CASES) takes them over in round 2, once they have
+# been run on a B200.
+_OPT_TEXT = b"Options: B200 {~}\n"
+OPTIONS = [
+    _case("opt-2start-2stop", _OPT_TEXT, ["1200", "--startbits", "2", "--stopbits", "2.0"],
+          mkw=dict(startbits=2, stopbits=2.0), audio=True),
+    _case("opt-stop-1.5", _OPT_TEXT, ["1200", "--stopbits", "1.5"], mkw=dict(stopbits=1.5), audio=True),
+    _case("opt-msb-first", _OPT_TEXT, ["1200", "--msb-first"], mkw=dict(msb_first=True), audio=True),
+    _case("opt-7bit-msb-first", _OPT_TEXT, ["-7", "1200", "--msb-first"],
+          mkw=dict(n_data_bits=7, msb_first=True), audio=True),
+    _case("opt-invert-start-stop", _OPT_TEXT, ["1200", "--invert-start-stop"],
+          mkw=dict(invert_start_stop=True), audio=True),
+    _case("opt-inverted", _OPT_TEXT, ["1200", "--inverted"], mkw=dict(inverted=True), audio=True),
+    _case("opt-sync-byte-600", _OPT_TEXT, ["600", "--sync-byte", "0x7E"], mode="600",
+          mkw=dict(sync_byte=0x7E), audio=True),
+    _case("opt-2400-44100", _OPT_TEXT, ["2400", "--samplerate", "44100"], mode="2400",
+          mkw=dict(sample_rate=44100), audio=True),
+    _case("opt-600-22050", _OPT_TEXT, ["600", "--samplerate", "22050"], mode="600",
+          mkw=dict(sample_rate=22050), audio=True),
+    _case("opt-300-bandwidth-25", _OPT_TEXT, ["300", "-b", "25"], mode="300", mkw=dict(bandwidth=25.0),
+          audio=True),
+    _case("opt-110-baudot", b"RYRY 5-BIT AT 110\n", ["110", "-5"], mode="110", mkw=dict(baudot=True),
+          audio=True),
+    _case("opt-thresholds", _OPT_TEXT, ["1200"], rx=["1200", "-c", "3.0", "-l", "4.0"],
+          rx_mkw=dict(confidence=3.0, limit=4.0), audio=True),
+    _case("opt-mark-space", _OPT_TEXT, ["1200", "-M", "1500", "-S", "2100"], mkw=dict(mark=1500, space=2100),
+          audio=True),
+]
+
+EVERY = ALL + OPTIONS
+BY_NAME = {c["name"]: c for c in EVERY}

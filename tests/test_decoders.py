@@ -200,6 +200,7 @@ KIND_OF = {"ascii8": "ascii8", "baudot": "baudot", "callerid": "callerid"}
 GOLD = [c for c in refcases.ALL if c["name"] in (
     "01-self-test-1200", "03-self-test-rtty", "60-multibyte", "70-callerid-mdmf", "71-callerid-sdmf",
     "80-SAME", "81-ascii7", "81-tdd", "21-rate-slop-308", "40-noise-0.50", "small-rtty", "small-same")]
+GOLD += refcases.OPTIONS
 
 
 @pytest.mark.parametrize("case", GOLD, ids=[c["name"] for c in GOLD])

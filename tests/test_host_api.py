@@ -43,19 +43,34 @@ MODES = [("1200", {}), ("300", {}), ("rtty", {}), ("tdd", {}), ("same", {}), ("c
          ("600", dict(sync_byte=0x7E))]
 
 
+# the option combinations minted from the reference CLI (tests/refcases.py OPTIONS), rx side
+MODES += [(c["rx_mode"], c["rx_mkw"]) for c in refcases.OPTIONS]
+
+
+def overrides_for(kw):
+    """orc.Mode keyword names -> fsk_b200_rx_config override names (the -5 option is n_data_bits 5)."""
+    names = dict(mark="f_mark", space="f_space", bandwidth="band_width", startbits="nstartbits",
+                 stopbits="nstopbits", confidence="confidence_threshold", limit="confidence_search_limit")
+    ov = {names.get(k, k): v for k, v in kw.items() if k not in ("sample_rate", "baudot")}
+    if kw.get("baudot"):
+        ov["n_data_bits"] = 5
+    return ov
+
+
 @pytest.mark.parametrize("mode,kw", MODES, ids=["%s-%d" % (m, i) for i, (m, _) in enumerate(MODES)])
 def test_presets_and_geometry_match_oracle(mode, kw):
     om = orc.Mode(mode, **kw)
     od = om.derived()
-    names = dict(mark="f_mark", space="f_space", bandwidth="band_width", startbits="nstartbits",
-                 stopbits="nstopbits")
-    ov = {names.get(k, k): v for k, v in kw.items() if k != "sample_rate"}
+    ov = overrides_for(kw)
     cfg = mm.rx_config_for_mode(mode, kw.get("sample_rate", 48000), **ov)
     assert np.float32(cfg.data_rate) == om.data_rate
     assert (np.float32(cfg.f_mark), np.float32(cfg.f_space)) == (om.mark_f, om.space_f)
     assert np.float32(cfg.band_width) == om.band_width
     assert (cfg.n_data_bits, cfg.nstartbits, np.float32(cfg.nstopbits)) == (om.n_data_bits, om.nstartbits, om.nstopbits)
     assert (cfg.do_rx_sync, cfg.sync_byte) == (om.do_rx_sync, om.sync_byte)
+    assert (cfg.invert_start_stop, cfg.msb_first) == (om.invert_start_stop, om.msb_first)
+    assert (np.float32(cfg.confidence_threshold), np.float32(cfg.confidence_search_limit)) == \
+        (om.confidence_threshold, om.confidence_search_limit)
     p = mm.rx_params(cfg)
     op = orc.Plan(om.sample_rate, om.mark_f, om.space_f, om.band_width).p
     assert (p.fftsize, p.nbands, p.b_mark, p.b_space) == (op.fftsize, op.nbands, op.b_mark, op.b_space)

@@ -9,7 +9,7 @@ import golden_util as gu
 import orc
 import refcases
 
-CASES = refcases.ALL
+CASES = refcases.EVERY
 IDS = [c["name"] for c in CASES]
 
 
