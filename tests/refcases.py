@@ -119,9 +119,21 @@ OPTIONS = [
           audio=True),
     _case("opt-thresholds", _OPT_TEXT, ["1200"], rx=["1200", "-c", "3.0", "-l", "4.0"],
           rx_mkw=dict(confidence=3.0, limit=4.0), audio=True),
+    _case("opt-binary-output", _OPT_TEXT, ["1200"], rx=["1200", "--binary-output"], audio=True),
+    _case("opt-rtty-binary-output", b"RYRY\n", ["rtty", "--samplerate", "8000"],
+          rx=["rtty", "--samplerate", "8000", "--binary-output"], mode="rtty", mkw=dict(sample_rate=8000),
+          audio=True),
     _case("opt-mark-space", _OPT_TEXT, ["1200", "-M", "1500", "-S", "2100"], mkw=dict(mark=1500, space=2100),
           audio=True),
 ]
+
+
+
+def decoder_of(case, rx_mode):
+    """The databits decoder the reference's main() ends up with for this rx invocation
+    (src/minimodem.c:552-892): --binary-output overrides the mode's."""
+    return "binary" if "--binary-output" in case["rx"] else rx_mode.decoder
+
 
 EVERY = ALL + OPTIONS
 BY_NAME = {c["name"]: c for c in EVERY}

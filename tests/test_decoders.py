@@ -196,7 +196,6 @@ def test_output_cap_counts_are_clamped_by_the_caller():
 # --------------------------------------------------------------------------
 # frame records of the rx-loop restatement -> the reference CLI's stdout
 # --------------------------------------------------------------------------
-KIND_OF = {"ascii8": "ascii8", "baudot": "baudot", "callerid": "callerid"}
 GOLD = [c for c in refcases.ALL if c["name"] in (
     "01-self-test-1200", "03-self-test-rtty", "60-multibyte", "70-callerid-mdmf", "71-callerid-sdmf",
     "80-SAME", "81-ascii7", "81-tdd", "21-rate-slop-308", "40-noise-0.50", "small-rtty", "small-same")]
@@ -210,17 +209,17 @@ def test_records_decode_to_reference_stdout(case):
     a = gu.audio(case, g)
     r = orc.rx_run(rx, a, literal=False, rxnoise=case["rxnoise"], rx_one=case["rx_one"])
     rec = orc.frame_records(r["frames"])
-    got = orc.decode_records(rx, KIND_OF[rx.decoder], rec)
+    kind = refcases.decoder_of(case, rx)
+    got = orc.decode_records(rx, kind, rec)
     assert got == bytes(g["stdout"])
     # a stream decoded in two batches continues where it stopped
     st = orc.DecoderState()
     k = rec.shape[0] // 2
-    two = orc.decode_records(rx, KIND_OF[rx.decoder], rec[:k], state=st) + \
-        orc.decode_records(rx, KIND_OF[rx.decoder], rec[k:], state=st)
+    two = orc.decode_records(rx, kind, rec[:k], state=st) + orc.decode_records(rx, kind, rec[k:], state=st)
     assert two == got
     # session reports in the record stream are skipped
     mixed = np.insert(rec, k, np.array([1, 2, 3, 4, orc.FRAME_REPORT], np.uint32), axis=0)
-    assert orc.decode_records(rx, KIND_OF[rx.decoder], mixed) == got
+    assert orc.decode_records(rx, kind, mixed) == got
 
 
 def test_decoder_choice_follows_the_reference_main():

@@ -51,7 +51,7 @@ def test_rx_restatement_decodes_and_reports_like_reference(case):
     a = gu.audio(case, g)
     for literal in (True, False):
         r = orc.rx_run(rx, a, literal=literal, rxnoise=case["rxnoise"], rx_one=case["rx_one"])
-        out = orc.ref_decode(rx, r["frames"])
+        out = orc.ref_decode(rx, r["frames"], decoder=refcases.decoder_of(case, rx))
         assert out == bytes(g["stdout"]), ("literal" if literal else "flat")
         want = gu.stat_lines(g)
         got = [orc.report_line(rx, rp) for rp in r["reports"]]
