@@ -497,7 +497,6 @@ __device__ __forceinline__ float frame_analyze_fast(const Ring rg, unsigned cand
 	const float *q = p[0];
 #pragma unroll
 	for (int pp = 0; pp < L; pp++) {
-	    constexpr int dummy = 0; (void)dummy;
 	    const int j = pp + k * L;
 	    if (j < W && part == (unsigned)pp) {
 		if (!XCHG) {

@@ -176,21 +176,23 @@ k_find_frame(const __grid_constant__ fsk_b200_geom geo, const float4 *__restrict
 /* ------------------------------------------------------------------------ */
 
 /* FILL 0: cp.async (LDGSTS) by all lanes of the group; FILL 1: cp.async.bulk (TMA engine)
- * issued by lane 0 with mbarrier completion */
-/* ask for the next iteration's samples as soon as the searches of this one are over
- * (measured +3.6 % over asking at the top of the next iteration) */
+ * issued by lane 0 with mbarrier completion.
+ * EARLY_REQ (FILL 0): ask for the next iteration's samples as soon as the searches of this one
+ * are over (measured +3.6 % over asking at the top of the next iteration). */
 #ifdef FSK_NO_EARLY_REQ
 #define EARLY_REQ 0
 #else
 #define EARLY_REQ 1
 #endif
-template <int G, int W, int L, int MODE, int FILL>
+/* 128 threads x 4 blocks caps the kernel at 128 registers per thread: 8 blocks of 64 threads per
+ * SM, which is also what the shared-memory rings allow */
 #ifndef FSK_MINBLOCKS
 #define FSK_MINBLOCKS 4
 #endif
 #ifndef FSK_MAXTHREADS
 #define FSK_MAXTHREADS 128
 #endif
+template <int G, int W, int L, int MODE, int FILL>
 __global__ void __launch_bounds__(FSK_MAXTHREADS, FSK_MINBLOCKS)
 k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200_loopc lc,
 	const float4 *__restrict__ tw_global, unsigned tw_in_smem, unsigned ring_floats,
@@ -345,8 +347,10 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
 	    int ready = 0;
 	    bool pending = false;
 	    if (MODE == 0) {
-		/* prefetch what the NEXT iteration can need (it starts at most `lookahead`
-		 * samples further), then wait only for what THIS one needs */
+		/* The samples of this iteration were normally requested an iteration ago (EARLY_REQ,
+		 * below); whatever is missing -- first iteration of a launch, a restarted ring, the
+		 * bulk variant -- is requested here together with what the next iteration can need
+		 * (it starts at most `lookahead` samples further) */
 		const unsigned need_now = (pos + try_max - 1u + geo.span + 3u) & ~3u;
 		const bool late = filled < need_now;	/* part of this window is only now requested */
 		ready = (int)(filled - pos);		/* >= -3: what earlier requests cover */
