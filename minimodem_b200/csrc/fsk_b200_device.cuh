@@ -264,6 +264,7 @@ __device__ __forceinline__ unsigned ring_wrap(unsigned off, unsigned R) { return
 /* Fast-path arithmetic: sqrt.approx / div.approx (<= 2 ulp) instead of the IEEE sequences.
  * They feed magnitudes and the confidence statistic, which are compared to tolerance; the
  * generic path keeps IEEE operations. */
+#ifndef FSK_EMU	/* inline PTX: the host emulation of the test harness (tests/emu) brings its own */
 __device__ __forceinline__ float fast_sqrt(float x)
 {
     float r;
@@ -278,6 +279,7 @@ __device__ __forceinline__ float fast_div(float a, float b)
     asm("div.approx.ftz.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
     return r;
 }
+#endif
 
 /* butterfly all-reduce over the G lanes of a group (every lane ends with the total) */
 template <int G>
@@ -305,9 +307,11 @@ __device__ __forceinline__ unsigned group_add(unsigned v, unsigned gmask)
     return v;
 }
 
+#ifndef FSK_EMU	/* inline PTX, see tests/emu */
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int NKEEP>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" :: "n"(NKEEP) : "memory"); }
+#endif
 
 /* What a lane needs to know about its W windows, computed once per kernel instead of per
  * candidate: the offset of each window inside a frame candidate, which of them this lane
@@ -689,6 +693,7 @@ __device__ __noinline__ Found find_frame_fast(const Ring rg, unsigned pos_off,
 /* ------------------------------------------------------------------------ */
 
 
+#ifndef FSK_EMU	/* inline PTX, see tests/emu */
 __device__ __forceinline__ void ldgsts16(unsigned dst, const float *src)
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" :: "r"(dst), "l"(src) : "memory");
@@ -697,6 +702,7 @@ __device__ __forceinline__ void ldgsts16_zfill(unsigned dst, const float *src, u
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" :: "r"(dst), "l"(src), "r"(valid) : "memory");
 }
+#endif
 
 /* one linear run of `count` floats (multiple of 4): lanes take 16-byte chunks round-robin */
 template <int G>
@@ -829,6 +835,7 @@ __device__ __forceinline__ void ring_block_tail(const Ring rg, unsigned ring_s, 
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 
+#ifndef FSK_EMU	/* inline PTX, see tests/emu */
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" :: "r"(bar), "r"(count) : "memory");
@@ -850,6 +857,7 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity)
 	    "selp.u32 %0, 1, 0, p;\n}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     return ok != 0;
 }
+#endif
 /* bounded spin: a byte-count bug must end in a trapped kernel, never a hung GPU */
 __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
 {
@@ -857,11 +865,13 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
 	if (spin > (1u << 24))
 	    __trap();
 }
+#ifndef FSK_EMU	/* inline PTX, see tests/emu */
 __device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
 	    :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+#endif
 
 /* Lane 0 of the group copies absolute indices [from, to) (multiples of 4, to <= the
  * 4-rounded valid length, to - (pos & ~3) <= R) into the ring and its mirror with at

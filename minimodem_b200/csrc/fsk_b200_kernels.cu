@@ -44,6 +44,14 @@
 
 static unsigned long long g_launches;
 
+/* Kernel launch and dynamic shared memory go through two macros so that the test harness
+ * (tests/emu: the same source compiled for the host under a SIMT emulator) can substitute its
+ * own; the product build is plain CUDA. */
+#ifndef FSK_EMU
+#define FSK_LAUNCH(kernel, grid, block, smem, stream, ...) kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__)
+#define FSK_DYN_SMEM(name) extern __shared__ float4 name[]
+#endif
+
 #define CUDA_TRY(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
     fsk_b200_set_error("%s: %s", #call, cudaGetErrorString(e_)); return -EIO; } } while (0)
 
@@ -125,7 +133,7 @@ __global__ void __launch_bounds__(256)
 k_find_frame(const __grid_constant__ fsk_b200_geom geo, const float4 *__restrict__ tw_global,
 	unsigned tw_in_smem, unsigned ring_floats, const __grid_constant__ FindArgs a)
 {
-    extern __shared__ float4 smem4[];
+    FSK_DYN_SMEM(smem4);
     const Smem sm = carve<G>(smem4, geo, tw_global, tw_in_smem, ring_floats);
     GROUP_VARS;
     const Ring rg = { smem_u32(sm.ring), ring_floats, (geo.bit_nsamples + 3u) & ~3u };
@@ -198,7 +206,7 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
 	const float4 *__restrict__ tw_global, unsigned tw_in_smem, unsigned ring_floats,
 	unsigned lookahead, const __grid_constant__ RxArgs a)
 {
-    extern __shared__ float4 smem4[];
+    FSK_DYN_SMEM(smem4);
     const Smem sm = carve<G>(smem4, geo, tw_global, tw_in_smem, ring_floats);
     GROUP_VARS;
     const Ring rg = { smem_u32(sm.ring), ring_floats, (geo.bit_nsamples + 3u) & ~3u };
@@ -550,7 +558,7 @@ k_rx_ws(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b
 	const float4 *__restrict__ tw_global, unsigned ring_floats, unsigned lookahead,
 	const __grid_constant__ RxArgs a)
 {
-    extern __shared__ float4 smem4[];
+    FSK_DYN_SMEM(smem4);
     const Smem sm = carve<G>(smem4, geo, tw_global, 1u, ring_floats);
     GROUP_VARS;
     const Ring rg = { smem_u32(sm.ring), ring_floats, (geo.bit_nsamples + 3u) & ~3u };
@@ -1234,7 +1242,7 @@ static cudaError_t launch_find_t(const Shape &sh, const CudaEngine *ce, const Fi
 	    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh.smem);
     if (e != cudaSuccess)
 	return e;
-    k_find_frame<G, W, L, MODE><<<sh.blocks, sh.wpb * 32, sh.smem, st>>>(sh.geo, ce->d_tw,
+    FSK_LAUNCH((k_find_frame<G, W, L, MODE>), sh.blocks, sh.wpb * 32, sh.smem, st, sh.geo, ce->d_tw,
 	    sh.tw_in_smem, sh.ring, a);
     g_launches++;
     return cudaGetLastError();
@@ -1280,7 +1288,7 @@ static cudaError_t launch_rx_ws_t(const Shape &sh, const CudaEngine *ce, const f
 	    (int)sh.smem);
     if (e != cudaSuccess)
 	return e;
-    k_rx_ws<G, W, L><<<sh.blocks, sh.wpb * 32, sh.smem, st>>>(sh.geo, *lc, ce->d_tw, sh.ring,
+    FSK_LAUNCH((k_rx_ws<G, W, L>), sh.blocks, sh.wpb * 32, sh.smem, st, sh.geo, *lc, ce->d_tw, sh.ring,
 	    sh.lookahead, a);
     g_launches++;
     return cudaGetLastError();
@@ -1294,8 +1302,8 @@ static cudaError_t launch_rx_t(const Shape &sh, const CudaEngine *ce, const fsk_
 	    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh.smem);
     if (e != cudaSuccess)
 	return e;
-    k_rx<G, W, L, MODE, FILL><<<sh.blocks, sh.wpb * 32, sh.smem, st>>>(sh.geo, *lc, ce->d_tw, sh.tw_in_smem,
-	    sh.ring, sh.lookahead, a);
+    FSK_LAUNCH((k_rx<G, W, L, MODE, FILL>), sh.blocks, sh.wpb * 32, sh.smem, st, sh.geo, *lc, ce->d_tw,
+	    sh.tw_in_smem, sh.ring, sh.lookahead, a);
     g_launches++;
     return cudaGetLastError();
 }
@@ -1434,10 +1442,10 @@ extern "C" int fsk_b200_cuda_s16_to_f32(const int16_t *src, float *dst, size_t n
 	return 0;
     if ((n & 7) == 0 && ((uintptr_t)src & 15) == 0) {
 	const size_t n8 = n / 8;
-	k_s16_to_f32<<<(unsigned)((n8 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+	FSK_LAUNCH(k_s16_to_f32, (unsigned)((n8 + 255) / 256), 256, 0, (cudaStream_t)stream,
 		reinterpret_cast<const int4 *>(src), reinterpret_cast<float4 *>(dst), n8);
     } else {
-	k_s16_to_f32_scalar<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, dst, n);
+	FSK_LAUNCH(k_s16_to_f32_scalar, (unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream, src, dst, n);
     }
     g_launches++;
     cudaError_t e = cudaGetLastError();
@@ -1458,7 +1466,7 @@ extern "C" int fsk_b200_cuda_decode(int kind, unsigned shift, unsigned n_data_bi
 	return 0;
     const unsigned blocks = (unsigned)((nstreams + 127) / 128);
     cudaStream_t st = (cudaStream_t)stream;
-#define DECODE_CASE(K) case K: k_decode<K><<<blocks, 128, 0, st>>>(shift, n_data_bits, msb_first, \
+#define DECODE_CASE(K) case K: FSK_LAUNCH(k_decode<K>, blocks, 128, 0, st, shift, n_data_bits, msb_first, \
 	    do_rx_sync, sync_byte, frames, states, (unsigned)nstreams, max_frames, dstates, out, \
 	    out_stride, out_count); break
     switch (kind) {
@@ -1534,7 +1542,8 @@ extern "C" int fsk_b200_cuda_band_mags(void *p, int fftsize, const float *host_s
 	ce->d_mags_cap = nbands;
     }
     CUDA_TRY(cudaMemcpy(ce->d_one, host_samples, (size_t)nsamples * sizeof(float), cudaMemcpyHostToDevice));
-    k_band_mags<<<(nbands + 127) / 128, 128>>>(ce->d_one, nsamples, fftsize, nbands, ce->d_mags);
+    FSK_LAUNCH(k_band_mags, (nbands + 127) / 128, 128, 0, (cudaStream_t)0, ce->d_one, nsamples, fftsize, nbands,
+	    ce->d_mags);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpy(host_mags, ce->d_mags, (size_t)nbands * sizeof(float), cudaMemcpyDeviceToHost));
@@ -1555,7 +1564,7 @@ extern "C" int fsk_b200_cuda_tx_batch(const fsk_b200_tx_config *cfg, const float
     L.rate = (unsigned)sample_rate;
     const unsigned threads = 128;
     const size_t blocks = (nstreams * 32 + threads - 1) / threads;
-    k_tx<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(*cfg, L, sin_table, table_len, words,
+    FSK_LAUNCH(k_tx, (unsigned)blocks, threads, 0, (cudaStream_t)stream, *cfg, L, sin_table, table_len, words,
 	    nwords, lead_in, samples_out, (unsigned)nstreams, stride, nsamples_out);
     g_launches++;
     cudaError_t e = cudaGetLastError();
