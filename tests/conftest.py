@@ -7,6 +7,13 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
+# FSK_B200_EMU=1: run the "gpu" tests on the host SIMT emulation of the kernels (tests/emu)
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "emu"))
+import emu_mode  # noqa: E402
+
+EMU_DEVICE = emu_mode.activate() if emu_mode.active() else None
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
     config.addinivalue_line("markers", "ref: needs oracle/_ref (the reference compiled in place)")

@@ -1,0 +1,38 @@
+"""The kernels' SOURCE on the host SIMT emulator (tests/emu): the parity tests that normally need
+a B200 (tests/test_gpu_parity.py, marker `gpu`) run here on CPU cores against the emulation
+build of the very same minimodem_b200/csrc/*.cu / *.cuh files.  It checks what an emulator can
+check -- control flow, ring bookkeeping, lane exchanges, cp.async ordering (copies land as late
+as the code's own waits allow, or at once), record and state formats, every decoder -- before
+GPU minutes are spent; timing, the approximate sqrt/div units and the hardware itself are
+checked only by the `gpu` run.  The emulation library is never loaded by the product."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def run_emulated(select, async_mode, timeout):
+    env = dict(os.environ, FSK_B200_EMU="1", FSK_EMU_ASYNC=async_mode)
+    env.pop("FSK_B200_LIB", None)
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"),
+                        "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider", "-k", select],
+                       cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=timeout)
+    tail = r.stdout.decode(errors="replace")[-3000:]
+    assert r.returncode == 0, tail
+    return tail
+
+
+def test_parity_suite_on_the_emulated_kernels_late_copies():
+    """Everything but the large round-trip batches; cp.async copies land only at the waits."""
+    tail = run_emulated("not roundtrip", "late", 1500)
+    assert " passed" in tail and "failed" not in tail
+
+
+def test_reference_vectors_on_the_emulated_kernels_eager_copies():
+    """The reference vectors and the resume/ragged cases with copies landing at issue: a copy
+    requested while its target is still being read would corrupt the window."""
+    tail = run_emulated("reference_vectors or edge_cases or overflow or lane_split", "eager", 900)
+    assert " passed" in tail and "failed" not in tail
