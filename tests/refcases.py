@@ -93,9 +93,7 @@ ALL = CASES + SMALL
 
 # Option combinations none of the reference's own tests use (framing, bit order, tone
 # inversion, sync byte, odd sample rates, thresholds): short payloads, audio committed.
-# Minted like the others from the unmodified reference CLI.  They pin the oracle (CPU tests);
-# the GPU list (tests/test_gpu_parity.py RX_CASES) takes them over in round 2, once they have
-# been run on a B200.
+# Minted like the others from the unmodified reference CLI; on the CPU and the GPU lists.
 _OPT_TEXT = b"Options: B200 {~}\n"
 OPTIONS = [
     _case("opt-2start-2stop", _OPT_TEXT, ["1200", "--startbits", "2", "--stopbits", "2.0"],
