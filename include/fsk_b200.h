@@ -236,6 +236,15 @@ int fsk_b200_rx_batch_host(fsk_b200_engine *e, const float *host_samples, size_t
 	fsk_b200_frame *host_frames, uint32_t max_frames,
 	fsk_b200_stream_state *host_states);
 
+/* N3, batched -- fsk_detect_carrier (src/fsk.c:543-581, the --auto-carrier probe of
+ * src/minimodem.c:1179-1220) for many streams in one launch: stream s is analysed over the
+ * nsamples (1..fftsize) floats at samples[s*stride + offset[s]] (offset may be NULL = 0), zero
+ * padded to fftsize; out_band[s] = the band (1..fftsize/2) with the largest magnitude among those
+ * >= min_mag_threshold, the lowest such band on a tie, or -1.  The caller applies
+ * fsk_set_tones_by_bandshift's rule per stream.  Device pointers. */
+int fsk_b200_detect_carrier_batch(int fftsize, const float *samples, size_t nstreams, size_t stride,
+	const uint32_t *offset, uint32_t nsamples, float min_mag_threshold, int32_t *out_band, void *stream);
+
 /* N2 -- 16-bit PCM ingest (the reference transmitter's default sample format, read back by
  * its rx as float = short / 32768: src/simpleaudio-sndfile.c:43-57, src/minimodem.c:786-788).
  * fsk_b200_s16_to_f32: device conversion (exact: a power-of-two scale), asynchronous on `stream`.

@@ -101,7 +101,7 @@ EXPORTS = [
     "fsk_b200_max_frames", "fsk_b200_frame_databits", "fsk_b200_tx_batch", "fsk_b200_sin_table",
     "fsk_b200_s16_to_f32", "fsk_b200_rx_batch_host_s16", "fsk_b200_decode_ascii_batch",
     "fsk_b200_decode_batch", "fsk_b200_decoder_for_mode", "fsk_b200_decode_max_bytes_per_frame",
-    "fsk_b200_decode_max_bytes",
+    "fsk_b200_decode_max_bytes", "fsk_b200_detect_carrier_batch",
     "fsk_b200_version", "fsk_b200_launch_count", "fsk_b200_last_error",
 ]
 
@@ -184,6 +184,9 @@ def lib():
     L.fsk_b200_decode_max_bytes_per_frame.restype = C.c_uint32
     L.fsk_b200_decode_max_bytes.argtypes = [C.c_int, C.c_uint, C.c_uint32]
     L.fsk_b200_decode_max_bytes.restype = C.c_uint64
+    L.fsk_b200_detect_carrier_batch.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p,
+                                                C.c_uint32, C.c_float, C.c_void_p, C.c_void_p]
+    L.fsk_b200_detect_carrier_batch.restype = C.c_int
     L.fsk_b200_sin_table.argtypes = [C.POINTER(C.c_float), C.c_uint, C.c_float]
     L.fsk_b200_sin_table.restype = None
     L.fsk_b200_version.restype = C.c_char_p
@@ -482,6 +485,21 @@ def decoder_for_mode(baudmode, n_data_bits=8, binary_output=False):
 
 def decode_max_bytes_per_frame(kind, n_data_bits):
     return int(lib().fsk_b200_decode_max_bytes_per_frame(int(kind), int(n_data_bits)))
+
+
+def detect_carrier_batch(fftsize, samples, nsamples, min_mag_threshold, offset=None, stream=None):
+    """fsk_b200_detect_carrier_batch: samples [nstreams, stride] float32 CUDA tensor (optional
+    per-stream uint32/int32 `offset` tensor) -> int32 CUDA tensor [nstreams] of band indices (-1 = none)."""
+    torch = _torch()
+    assert samples.is_cuda and samples.dtype == torch.float32 and samples.is_contiguous()
+    nstreams, stride = samples.shape
+    out = torch.empty((nstreams,), dtype=torch.int32, device=samples.device)
+    rc = lib().fsk_b200_detect_carrier_batch(int(fftsize), _ptr(samples), nstreams, stride, _ptr(offset),
+                                             int(nsamples), float(min_mag_threshold), _ptr(out),
+                                             _stream_handle(stream))
+    if rc:
+        _err("fsk_b200_detect_carrier_batch", rc)
+    return out
 
 
 def decode_max_bytes(kind, n_data_bits, nframes):

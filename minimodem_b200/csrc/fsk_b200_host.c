@@ -676,6 +676,25 @@ int fsk_detect_carrier(fsk_plan *fskp, float *samples, unsigned int nsamples,
     return best;
 }
 
+int fsk_b200_detect_carrier_batch(int fftsize, const float *samples, size_t nstreams, size_t stride,
+	const uint32_t *offset, uint32_t nsamples, float min_mag_threshold, int32_t *out_band, void *stream)
+{
+    if (!samples || !out_band || fftsize < 2) {
+	fsk_b200_set_error("detect_carrier_batch: NULL argument");
+	return -EINVAL;
+    }
+    if (nsamples == 0 || nsamples > (uint32_t)fftsize) {	/* the assert of src/fsk.c:547 */
+	fsk_b200_set_error("detect_carrier_batch: nsamples %u outside 1..fftsize %d", nsamples, fftsize);
+	return -EINVAL;
+    }
+    if (!fsk_b200_cuda_device_ok()) {
+	fsk_b200_set_error("no usable CUDA device (there is no CPU fallback)");
+	return -ENODEV;
+    }
+    return fsk_b200_cuda_detect_carrier_batch(fftsize, samples, nstreams, stride, offset, nsamples,
+	    min_mag_threshold, out_band, stream);
+}
+
 void fsk_set_tones_by_bandshift(fsk_plan *fskp, unsigned int b_mark, int b_shift)
 {
     assert(b_shift != 0);				/* src/fsk.c:587-592 */

@@ -22,7 +22,7 @@
  * k_rx<G,W,L,MODE,FILL>   the whole rx loop per stream (MODE 0 fast / 1 generic)
  * k_rx_ws<G,W,L>          the same, warp-synchronous (selectable, measured slower)
  * k_find_frame<G,W,L,MODE> batched fsk_find_frame
- * k_tx, k_band_mags, k_s16_to_f32, k_decode<KIND>   the "next" rows
+ * k_tx, k_band_mags, k_detect_carrier, k_s16_to_f32, k_decode<KIND>   the "next" rows
  *
  * Compiled with -fmad=false: every a*b+c below is either an explicit fmaf() (the
  * correlation sums) or two separately rounded operations, as in the reference's
@@ -763,14 +763,10 @@ k_rx_ws(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b
 /* full-spectrum magnitudes for fsk_detect_carrier (src/fsk.c:543-581)      */
 /* ------------------------------------------------------------------------ */
 
-__global__ void k_band_mags(const float *__restrict__ x, unsigned nsamples, int fftsize,
-	unsigned nbands, float *__restrict__ mags)
+/* magnitude of band k over the first nsamples of x, zero-padded to fftsize (src/fsk.c:549-553) */
+__device__ __forceinline__ float band_mag(const float *__restrict__ x, unsigned nsamples, unsigned F, unsigned k)
 {
-    const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= nbands)
-	return;
     double re = 0., im = 0.;
-    const unsigned F = (unsigned)fftsize;
     unsigned r = 0;				/* (k*n) mod F, kept exact in integers */
     for (unsigned n = 0; n < nsamples; n++) {
 	float sn, cs;
@@ -783,7 +779,52 @@ __global__ void k_band_mags(const float *__restrict__ x, unsigned nsamples, int 
     }
     const float magscalar = 1.0f / ((float)nsamples / 2.0f);	/* src/fsk.c:553 */
     const float fr = (float)re, fi = (float)im;
-    mags[k] = sqrtf(fr * fr + fi * fi) * magscalar;
+    return sqrtf(fr * fr + fi * fi) * magscalar;
+}
+
+__global__ void k_band_mags(const float *__restrict__ x, unsigned nsamples, int fftsize,
+	unsigned nbands, float *__restrict__ mags)
+{
+    const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nbands)
+	return;
+    mags[k] = band_mag(x, nsamples, (unsigned)fftsize, k);
+}
+
+/* N3, batched: fsk_detect_carrier (src/fsk.c:543-581) for one stream per warp.  The lanes take
+ * the bands 1, 2, ... round-robin; each keeps the first strictly largest magnitude at or above
+ * the threshold among its own (ascending) bands, and the warp then keeps the largest, the
+ * lowest band on a tie -- which is what the reference's single ascending scan picks. */
+__global__ void k_detect_carrier(const float *__restrict__ samples, unsigned nstreams, size_t stride,
+	const uint32_t *__restrict__ offset, unsigned nsamples, int fftsize, unsigned nbands,
+	float min_mag_threshold, int32_t *__restrict__ out_band)
+{
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (s >= nstreams)
+	return;						/* whole warps leave together */
+    const float *x = samples + (size_t)s * stride + (offset ? offset[s] : 0u);
+    float max_mag = 0.0f;
+    int best = -1;
+    for (unsigned k = 1 + lane; k < nbands; k += 32) {
+	const float m = band_mag(x, nsamples, (unsigned)fftsize, k);
+	if (m < min_mag_threshold)			/* :566 */
+	    continue;
+	if (max_mag < m) {				/* :570: strict, so the first of equals stays */
+	    max_mag = m;
+	    best = (int)k;
+	}
+    }
+    for (int o = 16; o; o >>= 1) {
+	const float om = __shfl_xor_sync(0xffffffffu, max_mag, o);
+	const int ob = __shfl_xor_sync(0xffffffffu, best, o);
+	if (ob >= 0 && (best < 0 || max_mag < om || (max_mag == om && ob < best))) {
+	    max_mag = om;
+	    best = ob;
+	}
+    }
+    if (lane == 0)
+	out_band[s] = best;
 }
 
 /* ------------------------------------------------------------------------ */
@@ -1547,6 +1588,26 @@ extern "C" int fsk_b200_cuda_band_mags(void *p, int fftsize, const float *host_s
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpy(host_mags, ce->d_mags, (size_t)nbands * sizeof(float), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int fsk_b200_cuda_detect_carrier_batch(int fftsize, const float *samples, size_t nstreams,
+	size_t stride, const uint32_t *offset, uint32_t nsamples, float min_mag_threshold,
+	int32_t *out_band, void *stream)
+{
+    if (nstreams == 0)
+	return 0;
+    const unsigned nbands = (unsigned)fftsize / 2u + 1u;
+    const unsigned threads = 128;
+    const size_t blocks = (nstreams * 32 + threads - 1) / threads;
+    FSK_LAUNCH(k_detect_carrier, (unsigned)blocks, threads, 0, (cudaStream_t)stream, samples, (unsigned)nstreams,
+	    stride, offset, nsamples, fftsize, nbands, min_mag_threshold, out_band);
+    g_launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+	fsk_b200_set_error("detect_carrier_batch launch: %s", cudaGetErrorString(e));
+	return -EIO;
+    }
     return 0;
 }
 

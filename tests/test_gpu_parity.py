@@ -285,6 +285,57 @@ def test_dropin_detect_carrier_and_bandshift():
     plan.destroy()
 
 
+@pytest.mark.parametrize("rate,bw,n", [(48000, 200.0, 40), (8000, 10.0, 176), (48000, 50.0, 160)])
+def test_detect_carrier_batch(rate, bw, n):
+    """N3 batched: one launch over many streams = the drop-in fsk_detect_carrier per stream
+    (same band arithmetic), = the unmodified reference's pick on streams with a clear carrier."""
+    plan = mm.FskPlan(rate, 1200.0 if rate == 48000 else 1585.0, 2200.0 if rate == 48000 else 1415.0, bw)
+    fftsize, nbands = plan.fftsize, plan.nbands
+    rng = np.random.default_rng(11)
+    nstreams, stride = 70, pad4(n + 24)
+    x = np.zeros((nstreams, stride), np.float32)
+    off = rng.integers(0, 20, nstreams).astype(np.int32)
+    t = np.arange(n, dtype=np.float32)
+    bands = rng.integers(1, nbands - 1, nstreams)
+    for s in range(nstreams):
+        f = bands[s] * rate / fftsize
+        amp = rng.uniform(0.2, 1.0)
+        y = amp * np.sin(2 * np.pi * f * t / rate + rng.uniform(0, 6.28)) + 0.02 * rng.standard_normal(n)
+        if s % 9 == 0:
+            y = 0.0 * y                                   # silence: no band reaches the threshold
+        x[s, off[s]:off[s] + n] = y.astype(np.float32)
+    d = torch.from_numpy(x).to(dev())
+    got = mm.detect_carrier_batch(fftsize, d, n, 0.05, offset=torch.from_numpy(off).to(dev()))
+    torch.cuda.synchronize()
+    got = got.cpu().numpy()
+    want_fn = None
+    if orc.have_ref():
+        rp = orc.RefPlan(rate, plan.f_mark, plan.f_space, bw)
+        want_fn = orc.ref().fsk_detect_carrier
+        want_fn.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_uint, C.c_float]
+        want_fn.restype = C.c_int
+    for s in range(nstreams):
+        w = np.ascontiguousarray(x[s, off[s]:off[s] + n])
+        assert got[s] == plan.detect_carrier(w, 0.05), s
+        if s % 9 == 0:
+            assert got[s] == -1
+        else:
+            # the window is n samples zero-padded to fftsize: the main lobe is fftsize/n bands wide
+            assert abs(int(got[s]) - int(bands[s])) <= fftsize // n + 1, (s, got[s], bands[s])
+        if want_fn is not None:
+            # two float DFTs may order two bands differently only when those are equal to rounding
+            k = np.arange(1, nbands)[:, None] * np.arange(n)[None, :]
+            m = np.abs((w[None, :].astype(np.float64) * np.exp(-2j * np.pi * k / fftsize)).sum(1))
+            top = np.sort(m)[-2:]
+            if top[1] == 0 or (top[1] - top[0]) / top[1] > 1e-4:
+                assert got[s] == want_fn(rp.h, orc.fptr(w), n, 0.05), s
+    # no offsets, threshold above everything
+    none = mm.detect_carrier_batch(fftsize, d, n, 10.0)
+    torch.cuda.synchronize()
+    assert (none.cpu().numpy() == -1).all()
+    plan.destroy()
+
+
 # --------------------------------------------------------------------------
 # transmitter model on the device: bit-exact with the oracle's restatement
 # --------------------------------------------------------------------------
