@@ -243,6 +243,7 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
 	bool tail_fix = false;				/* bulk fill: [n, n4) holds row padding, not zeros */
 
 	const unsigned ring_s = rg.ring_s;
+	unsigned landed = pos & ~3u;			/* absolute index up to which copies are known to have landed */
 	/* block fill: this lane's running source and destination (its first 16-byte chunk of
 	 * the block that starts at absolute index `filled`), carried instead of recomputed */
 	const unsigned dst0 = ring_s + 16u * g, dst_end = dst0 + R * 4u;
@@ -361,13 +362,16 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
 		 * (it starts at most `lookahead` samples further) */
 		const unsigned need_now = (pos + try_max - 1u + geo.span + 3u) & ~3u;
 		const bool late = filled < need_now;	/* part of this window is only now requested */
-		ready = (int)(filled - pos);		/* >= -3: what earlier requests cover */
+		/* what the previous search's wait has seen land (two-stage correlation only): the
+		 * requests made since -- the early one and the one below -- are still in flight */
+		ready = (int)(landed - pos);
 		if (FILL != 0 || !EARLY_REQ || late)	/* EARLY_REQ: normally asked for an iteration ago */
 		    request(min((pos + lookahead + need_max + 3u) & ~3u, (pos & ~3u) + R));
+		landed = filled;			/* true once this iteration's search has waited */
 		if (FILL == 0) {
 #if FSK_STAGE_J < 8
 		    settle(false);	/* two-stage correlation: the first stage needs the older copies */
-		    pending = late;
+		    pending = true;
 #else
 		    /* the search waits for all copies itself, right before its first correlation */
 		    (void)late;
@@ -518,6 +522,7 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
 		    /* skipped past everything requested so far: restart the ring here */
 		    drain();
 		    filled = pos & ~3u;
+		    landed = filled;
 		    pos_off = pos & 3u;
 		    fdst = dst0;
 		    fsrc = x + filled + 4u * g;
