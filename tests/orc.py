@@ -24,7 +24,8 @@ f32 = np.float32
 
 
 def build_oracle(force=False):
-    src = [os.path.join(ORACLE_DIR, f) for f in ("fsk_oracle.c", "fsk_oracle.h")]
+    src = [os.path.join(ORACLE_DIR, f) for f in ("fsk_oracle.c", "fsk_oracle.h", "decode_oracle.c")]
+    src.append(os.path.join(ROOT, "minimodem_b200", "csrc", "fsk_b200_decode_core.h"))
     if force or not os.path.exists(LIBORACLE) or any(
             os.path.getmtime(s) > os.path.getmtime(LIBORACLE) for s in src):
         subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "liboracle.so"])
