@@ -1,0 +1,74 @@
+"""Random modes through the emulated kernels (run by tests/test_emu_parity.py in a subprocess with
+FSK_B200_EMU=1; the file name keeps pytest from collecting it on its own).
+
+Framings, bit orders, rates and baud rates that no committed vector has: the oracle's transmitter
+makes the stream, the oracle's rx loop says what the records must be, the kernels' source (on the
+host SIMT emulator) has to produce them -- exact bits, frame starts and acquire flags, confidence
+and amplitude to the parity tolerance.  This is a logic check of the kernels over geometry the
+vectors do not reach (window counts from 7 to 44 bits, every lane split the launcher picks,
+fractional samples per bit, long windows); it runs on the emulator only, because a near-tie that
+the B200's approximate divide resolves the other way would make a random case flaky there."""
+import numpy as np
+import pytest
+
+import minimodem_b200 as mm
+import orc
+import test_gpu_parity as T
+
+pytestmark = pytest.mark.gpu
+
+BAUDS = [75, 110, 150, 300, 600, 1200, 2400, 4800]
+RATES = [8000, 11025, 16000, 22050, 44100, 48000]
+
+
+def random_mode(rng):
+    while True:
+        baud = int(rng.choice(BAUDS))
+        rate = int(rng.choice(RATES))
+        spb = rate / baud
+        if spb < 6 or spb > 700:
+            continue
+        kw = dict(sample_rate=rate)
+        kw["n_data_bits"] = int(rng.choice([5, 6, 7, 8, 9, 12, 16, 24, 32]))
+        kw["startbits"] = int(rng.choice([1, 1, 2, 3, 5]))
+        kw["stopbits"] = float(rng.choice([1.0, 1.0, 1.5, 2.0, 3.0]))
+        kw["msb_first"] = bool(rng.integers(0, 2))
+        kw["invert_start_stop"] = bool(rng.integers(0, 2))
+        kw["inverted"] = bool(rng.integers(0, 2))
+        if kw["n_data_bits"] + kw["startbits"] + kw["stopbits"] + 1 > 48:
+            continue
+        try:
+            m = orc.Mode(str(baud), **kw)
+            m.derived()
+            orc.Plan(m.sample_rate, m.mark_f, m.space_f, m.band_width)
+        except Exception:
+            continue
+        if max(m.mark_f, m.space_f) >= rate / 2 - m.band_width:
+            continue
+        return str(baud), kw
+
+
+@pytest.mark.parametrize("seed", range(64))
+def test_random_mode_records_match_the_oracle(seed):
+    rng = np.random.default_rng(1000 + seed)
+    mode, kw = random_mode(rng)
+    rx = orc.Mode(mode, **kw)
+    nwords = int(rng.integers(6, 18))
+    words = rng.integers(0, 1 << rx.n_data_bits, nwords, dtype=np.uint64).astype(np.uint32)
+    streams = []
+    for s in range(3):
+        a = orc.tx_words(rx, words, float(rng.uniform(0.3, 1.0)), 4096, True)
+        lead = int(rng.integers(0, 3 * int(rx.derived().nsamples_per_bit) + 1))
+        x = np.concatenate([np.zeros(lead, np.float32), a])
+        x = (x + np.float32(0.01) * rng.standard_normal(x.size).astype(np.float32)).astype(np.float32)
+        streams.append(x)
+    eng, _ = T.engine_for((mode, kw))
+    recs, st = T.rx_on_gpu(eng, streams)
+    decoded = 0
+    for s, x in enumerate(streams):
+        want = orc.rx_run(rx, x, literal=False)
+        got = T.as_oracle_frames(recs[s])
+        T.compare_frames(got, want["frames"], "%s %r stream %d" % (mode, kw, s))
+        T.compare_reports(T.reports_of(recs[s], st[s]), want["reports"], "%s %r stream %d" % (mode, kw, s))
+        decoded += len(got)
+    assert decoded >= nwords, (mode, kw, decoded, nwords)

@@ -14,10 +14,10 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def run_emulated(select, async_mode, timeout):
+def run_emulated(select, async_mode, timeout, module="test_gpu_parity.py"):
     env = dict(os.environ, FSK_B200_EMU="1", FSK_EMU_ASYNC=async_mode)
     env.pop("FSK_B200_LIB", None)
-    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"),
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", module),
                         "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider", "-k", select],
                        cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=timeout)
     tail = r.stdout.decode(errors="replace")[-3000:]
@@ -36,3 +36,10 @@ def test_reference_vectors_on_the_emulated_kernels_eager_copies():
     requested while its target is still being read would corrupt the window."""
     tail = run_emulated("reference_vectors or edge_cases or overflow or lane_split", "eager", 900)
     assert " passed" in tail and "failed" not in tail
+
+
+def test_random_modes_on_the_emulated_kernels():
+    """tests/emu_fuzz.py: 64 random framings / rates / bit orders, oracle TX -> emulated kernels
+    -> records equal to the oracle's rx loop."""
+    tail = run_emulated("random_mode", "late", 900, module="emu_fuzz.py")
+    assert "64 passed" in tail
