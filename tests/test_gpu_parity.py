@@ -714,3 +714,49 @@ def test_rx_then_device_decode_prints_what_the_reference_printed(name):
     o, c = out.cpu().numpy(), cnt.cpu().numpy()
     for s in range(2):
         assert bytes(o[s, :c[s]]) == bytes(g["stdout"]), s
+
+
+def test_uic_frames_end_to_end():
+    """UIC-751-3 (src/minimodem.c:859-875): 47-bit frames behind the fixed pattern 11110010, the
+    longest expect string of the reference.  It has no transmitter there, so the stream is made bit
+    by bit with the oracle's tone generator; samples in, text out on the device."""
+    rx = orc.Mode("uic-ground")
+    bitm = orc.Mode("600", mark=rx.mark_f, space=rx.space_f, n_data_bits=1, startbits=0, stopbits=0.0)
+
+    def frame_bits(train, code):
+        word = train | (int("{:08b}".format(code)[::-1], 2) << 24)
+        return [int(c) for c in "11110010"] + [(word >> i) & 1 for i in range(39)]
+
+    msgs = [(0x123456, 0x09), (0x654321, 0x55), (0xABCDEF, 0x02), (0x000001, 0x7E), (0x13579B, 0x0C)]
+    rng = np.random.default_rng(21)
+    streams = []
+    for s in range(4):
+        bits = [1] * int(rng.integers(12, 40))
+        for t, c in msgs[s:] + msgs[:s]:
+            bits += frame_bits(t, c)                          # frames follow each other directly
+        bits += [1] * 30
+        a = orc.tx_words(bitm, np.array(bits, np.uint32), float(rng.uniform(0.4, 1.0)), 4096, True)
+        streams.append((a + np.float32(0.005) * rng.standard_normal(a.size).astype(np.float32)).astype(np.float32))
+    for mode, kind in (("uic-ground", mm.DECODE_UIC_GROUND), ("uic-train", mm.DECODE_UIC_TRAIN)):
+        eng, _ = engine_for((mode, {}))
+        n = max(len(a) for a in streams)
+        buf = np.zeros((len(streams), pad4(n)), np.float32)
+        lens = np.zeros(len(streams), np.int32)
+        for i, a in enumerate(streams):
+            buf[i, :len(a)] = a
+            lens[i] = len(a)
+        frames, states = eng.rx_batch(torch.from_numpy(buf).to(dev()), nsamples=n,
+                                      nsamples_each=torch.from_numpy(lens).to(dev()))
+        out, cnt = eng.decode_batch(kind, frames, states)
+        torch.cuda.synchronize()
+        fr, st = mm.frames_to_numpy(frames), mm.states_to_numpy(states)
+        o, c = out.cpu().numpy(), cnt.cpu().numpy()
+        for s, a in enumerate(streams):
+            want = orc.rx_run(rx, a, literal=False)
+            compare_frames(as_oracle_frames(fr[s, :st["nframes"][s]]), want["frames"], "%s stream %d" % (mode, s))
+            text = bytes(o[s, :c[s]])
+            assert text == orc.decode_records(rx, "uic-ground" if kind == mm.DECODE_UIC_GROUND else "uic-train",
+                                              orc.frame_records(want["frames"]))
+            assert text.count(b"Train ID: ") == len(msgs), text
+        if kind == mm.DECODE_UIC_GROUND:
+            assert b"Train ID: 654321 - Message: 09 (Emergency stop)\n" in bytes(o[0, :c[0]])
