@@ -993,6 +993,7 @@ struct CudaEngine {
     fsk_b200_frame *d_slab_frames[2];
     fsk_b200_stream_state *d_slab_states[2];
     size_t slab_streams, slab_stride, slab_max_frames;
+    size_t slab_bytes;			/* host-buffer path: sample bytes per slab (FSK_B200_SLAB_BYTES) */
     cudaStream_t st[2];
 };
 
@@ -1027,6 +1028,8 @@ extern "C" void *fsk_b200_cuda_engine_new(void)
     if ((e = getenv("FSK_B200_SPLIT"))) ce->split = atoi(e);
     ce->fill = 0;		/* see the dispatch in fsk_b200_cuda_rx_batch */
     if ((e = getenv("FSK_B200_FILL"))) ce->fill = atoi(e);
+    ce->slab_bytes = (size_t)256 << 20;
+    if ((e = getenv("FSK_B200_SLAB_BYTES")) && atoll(e) > 0) ce->slab_bytes = (size_t)atoll(e);
     return ce;
 }
 
@@ -1410,8 +1413,8 @@ static int rx_batch_host_common(CudaEngine *ce, const fsk_b200_geom *g, const fs
 	const void *host_samples, int elem, size_t nstreams, size_t stride, uint32_t nsamples_all,
 	fsk_b200_frame *host_frames, uint32_t max_frames, fsk_b200_stream_state *host_states)
 {
-    /* slab = as many streams as fit ~256 MiB of float samples */
-    size_t slab = ((size_t)256 << 20) / (stride * sizeof(float));
+    /* slab = as many streams as fit ~256 MiB of float samples (two slabs in flight) */
+    size_t slab = ce->slab_bytes / (stride * sizeof(float));
     if (slab < 1) slab = 1;
     if (slab > nstreams) slab = nstreams;
     if (ce->slab_streams < slab || ce->slab_stride != stride || ce->slab_max_frames < max_frames) {

@@ -760,3 +760,38 @@ def test_uic_frames_end_to_end():
             assert text.count(b"Train ID: ") == len(msgs), text
         if kind == mm.DECODE_UIC_GROUND:
             assert b"Train ID: 654321 - Message: 09 (Emergency stop)\n" in bytes(o[0, :c[0]])
+
+
+@pytest.mark.parametrize("fmt", ["f32", "s16"])
+def test_host_buffer_path_in_many_slabs(fmt, monkeypatch):
+    """fsk_b200_rx_batch_host splits a batch into slabs of ~256 MiB and keeps two in flight; with the
+    slab shrunk to two streams, 7 streams take 4 slabs (the last one partial) on alternating
+    buffers -- records and states must equal the one-launch device path, stream by stream."""
+    case = refcases.BY_NAME["small-1200"]
+    g = gu.load(case["name"])
+    a = gu.audio(case, g)
+    rng = np.random.default_rng(2)
+    n = a.size + 600
+    stride = pad4(n)
+    nstreams = 7
+    hf = np.zeros((nstreams, stride), np.float32)
+    for s in range(nstreams):
+        lead = int(rng.integers(0, 600))
+        hf[s, lead:lead + a.size] = a * np.float32(rng.integers(2, 9) / 8.0)
+    hs = np.round(hf * 32768.0).astype(np.int16)
+    hf = hs.astype(np.float32) * np.float32(1 / 32768.0)       # the float streams ARE the int16 ones
+    monkeypatch.setenv("FSK_B200_SLAB_BYTES", str(2 * stride * 4))
+    eng, _ = engine_for(case)
+    monkeypatch.delenv("FSK_B200_SLAB_BYTES")
+    ref_eng, _ = engine_for(case)
+    frames, states = ref_eng.rx_batch(torch.from_numpy(hf).to(dev()), nsamples=n)
+    torch.cuda.synchronize()
+    want_fr, want_st = mm.frames_to_numpy(frames), mm.states_to_numpy(states)
+    if fmt == "f32":
+        fr, st = eng.rx_batch_host(hf, nsamples=n)
+    else:
+        fr, st = eng.rx_batch_host_s16(hs, nsamples=n)
+    assert np.array_equal(st, want_st)
+    for s in range(nstreams):
+        k = int(want_st["nframes"][s])
+        assert k > 0 and np.array_equal(fr[s, :k], want_fr[s, :k]), s
