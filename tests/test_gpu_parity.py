@@ -795,3 +795,56 @@ def test_host_buffer_path_in_many_slabs(fmt, monkeypatch):
     for s in range(nstreams):
         k = int(want_st["nframes"][s])
         assert k > 0 and np.array_equal(fr[s, :k], want_fr[s, :k]), s
+
+
+# --------------------------------------------------------------------------
+# the drop-in boundary end to end: the unmodified reference CLI on this library
+# --------------------------------------------------------------------------
+def _write_wav(path, samples, rate, as_float):
+    import struct
+    if as_float:
+        data, fmt, bits = samples.astype("<f4").tobytes(), 3, 32
+    else:
+        data, fmt, bits = np.round(samples * 32768.0).astype("<i2").tobytes(), 1, 16
+    hdr = b"RIFF" + struct.pack("<I", 36 + len(data)) + b"WAVE" + b"fmt " + struct.pack(
+        "<IHHIIHH", 16, fmt, 1, rate, rate * bits // 8, bits // 8, bits) + b"data" + struct.pack("<I", len(data))
+    with open(path, "wb") as f:
+        f.write(hdr + data)
+
+
+CLI_CASES = [c for c in refcases.EVERY if c["audio"]]
+
+
+@pytest.mark.parametrize("case", CLI_CASES, ids=[c["name"] for c in CLI_CASES])
+def test_reference_cli_on_this_library(case, tmp_path):
+    """oracle/_ref/minimodem_dropin = the reference's own main(), rx loop, decoders and src/fsk.h,
+    compiled unmodified and linked against libfsk_b200.so instead of src/fsk.c + FFTW.  On the
+    audio of the committed vectors it must print what the reference printed: stdout byte for byte,
+    the stat lines field for field (confidence to tolerance)."""
+    import os
+    import subprocess
+    import conftest
+    exe = os.path.join(os.path.dirname(orc.LIBREF), "minimodem_dropin")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/minimodem_dropin not built (needs /root/reference at build time)")
+    g = gu.load(case["name"])
+    a = gu.audio(case, g)
+    rate = int(g["audio_len"][1])
+    wav = str(tmp_path / "x.wav")
+    _write_wav(wav, a, rate, bool(g["audio_len"][2]))
+    env = dict(os.environ)
+    if conftest.EMU_DEVICE is not None:         # FSK_B200_EMU=1: the emulation build answers to the library's name
+        import test_dropin_cli
+        env["LD_LIBRARY_PATH"] = test_dropin_cli.emulation_as_product()
+    r = subprocess.run([exe, "--rx", "--file", wav] + list(case["rx"]), env=env, stdout=subprocess.PIPE,
+                       stderr=subprocess.PIPE, timeout=600)
+    assert r.returncode == 0, r.stderr[-500:]
+    assert r.stdout == bytes(g["stdout"])
+    got = [ln for ln in r.stderr.decode().splitlines() if ln.startswith("### NOCARRIER")]
+    want = gu.stat_lines(g)
+    assert len(got) == len(want)
+    for x, y in zip(got, want):
+        fa, fb = x.split(), y.split()
+        assert fa[:3] == fb[:3] and fa[4:] == fb[4:], (x, y)
+        ca, cb = float(fa[3].split("=")[1]), float(fb[3].split("=")[1])
+        assert gu.close(ca, cb, 2e-3, cond=gu.CONF_COND) or (np.isinf(ca) and np.isinf(cb)), (x, y)
