@@ -134,4 +134,15 @@ def decoder_of(case, rx_mode):
 
 
 EVERY = ALL + OPTIONS
-BY_NAME = {c["name"]: c for c in EVERY}
+
+# Runs that only the whole CLI can make (the oracle's rx loop has no --auto-carrier): they pin the
+# drop-in binary (the reference's main() on this library), tests/test_gpu_parity.py
+# test_reference_cli_on_this_library and tests/test_dropin_cli.py.
+CLI_ONLY = [
+    _case("cli-auto-carrier", b"auto carrier probe 0123456789\n", ["1200", "-M", "1600", "-S", "2600"],
+          rx=["1200", "--auto-carrier"], audio=True),
+    _case("cli-auto-carrier-rtty", b"RYRY AUTO\n", ["rtty", "--samplerate", "8000", "-M", "1000", "-S", "830"],
+          rx=["rtty", "--samplerate", "8000", "--auto-carrier"], mode="rtty", mkw=dict(sample_rate=8000), audio=True),
+]
+
+BY_NAME = {c["name"]: c for c in EVERY + CLI_ONLY}

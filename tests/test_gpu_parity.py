@@ -812,7 +812,7 @@ def _write_wav(path, samples, rate, as_float):
         f.write(hdr + data)
 
 
-CLI_CASES = [c for c in refcases.EVERY if c["audio"]]
+CLI_CASES = [c for c in refcases.EVERY + refcases.CLI_ONLY if c["audio"]]
 
 
 @pytest.mark.parametrize("case", CLI_CASES, ids=[c["name"] for c in CLI_CASES])
