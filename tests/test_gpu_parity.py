@@ -848,3 +848,31 @@ def test_reference_cli_on_this_library(case, tmp_path):
         assert fa[:3] == fb[:3] and fa[4:] == fb[4:], (x, y)
         ca, cb = float(fa[3].split("=")[1]), float(fb[3].split("=")[1])
         assert gu.close(ca, cb, 2e-3, cond=gu.CONF_COND) or (np.isinf(ca) and np.isinf(cb)), (x, y)
+
+
+def test_batched_entry_points_reject_bad_arguments():
+    """EINVAL with a message, never a launch: rows that are not 16-byte aligned, missing output
+    arrays, zero-sized record buffers, unknown decoders, detect windows longer than the transform."""
+    import errno
+    eng, cfg = engine_for(("1200", {}))
+    L = mm.lib()
+    x = torch.zeros((4, 4096), dtype=torch.float32, device=dev())
+    fr = torch.zeros((4, 16, 5), dtype=torch.int32, device=dev())
+    st = torch.zeros((4, mm.STATE_WORDS), dtype=torch.int32, device=dev())
+    p = lambda t: C.c_void_p(t.data_ptr())
+    before = mm.launch_count()
+    bad = [
+        L.fsk_b200_rx_batch(eng._e, p(x), 4, 4095, None, 4095, p(fr), 16, p(st), None),       # stride % 4
+        L.fsk_b200_rx_batch(eng._e, C.c_void_p(x.data_ptr() + 4), 4, 4092, None, 4000, p(fr), 16, p(st), None),
+        L.fsk_b200_rx_batch(eng._e, p(x), 4, 4096, None, 4096, None, 16, p(st), None),        # no record array
+        L.fsk_b200_rx_batch(eng._e, p(x), 4, 4096, None, 4096, p(fr), 0, p(st), None),        # no room for records
+        L.fsk_b200_rx_batch(eng._e, None, 4, 4096, None, 4096, p(fr), 16, p(st), None),
+        L.fsk_b200_decode_batch(C.byref(eng.params), 17, p(fr), p(st), 4, 16, None, p(x), 64, p(st), None),
+        L.fsk_b200_decode_batch(C.byref(eng.params), 0, p(fr), p(st), 4, 16, None, p(x), 0, p(st), None),
+        L.fsk_b200_detect_carrier_batch(240, p(x), 4, 4096, None, 241, 0.1, p(st), None),
+        L.fsk_b200_detect_carrier_batch(240, p(x), 4, 4096, None, 0, 0.1, p(st), None),
+    ]
+    assert all(rc == -errno.EINVAL for rc in bad), bad
+    assert L.fsk_b200_last_error()
+    assert mm.launch_count() == before
+    assert L.fsk_b200_rx_batch(eng._e, p(x), 0, 4096, None, 4096, p(fr), 16, p(st), None) == 0   # empty batch
