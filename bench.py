@@ -91,31 +91,51 @@ def cpu_measure(a, x, mode, steps=1, warmup=0, kinds=None):
     """Times the CPU arm on `x`.  The thread count is chosen by measurement (all logical
     CPUs, half, a quarter): on the 2-socket hosts of this pool the FFT-based reference
     stops scaling well before all 128 hyper-threads are busy, and the best of the three
-    is reported with the thread count that achieved it."""
+    is reported with the thread count that achieved it.
+
+    kind "reference" = the unmodified src/fsk.c.  Its speed is its FFT library's: it is timed on
+    MKL's DFTI (oracle/_ref/libfsk_ref_dfti.so, the closest thing to FFTW in this image; not
+    FFTW) when that loads, else on the portable scalar FFT stand-in, and the `sample` string
+    says which.  Both give the same frames (checked here on the sample: frame count and bit
+    checksum of every arm are compared with the first one's and reported)."""
     import orc
     cores = len(os.sched_getaffinity(0))
     kind = "reference" if orc.have_ref() else "port"
+    impl = {"port": "port", "reference": "reference"}
+    fft = "portable scalar mixed-radix FFT stand-in (not FFTW)"
+    if orc.have_ref() and orc.have_ref_dfti():
+        try:
+            orc.rx_many(mode, x[:1], nsamples=a.nsamples, nthreads=1, kind="reference-dfti")   # MKL start-up
+            impl["reference"] = "reference-dfti"
+            fft = "MKL DFTI FFT from libtorch_cpu.so as the FFTW stand-in (not FFTW)"
+        except Exception:
+            pass
     out = {}
+    check = None
     for k in (kinds or [kind]):
         best = None
         for nt in sorted({cores, max(1, cores // 2), max(1, cores // 4)}, reverse=True):
             ts = []
             for i in range(warmup + steps):
                 t = time.perf_counter()
-                total, fps, _ = orc.rx_many(mode, x, nsamples=a.nsamples, nthreads=nt, kind=k)
+                total, fps, bx = orc.rx_many(mode, x, nsamples=a.nsamples, nthreads=nt, kind=impl[k])
                 dt = time.perf_counter() - t
                 if i >= warmup:
                     ts.append(dt)
             dt = sum(ts) / len(ts)
             if best is None or dt < best[0]:
                 best = (dt, nt, int(total))
+            sig = (int(total), int(np.bitwise_xor.reduce(bx)))
+            if check is None:
+                check = sig
         dt, nt, total = best
         out[k] = dict(value=x.shape[0] * a.nsamples / dt / 1e6, unit="Msamples/s", cores=nt, kind=k,
                       sample="%d streams x %d samples, best of {%d, %d, %d} threads = %d, %s" % (
                           x.shape[0], a.nsamples, cores, max(1, cores // 2), max(1, cores // 4), nt,
-                          "unmodified src/fsk.c (oracle/_ref; FFT stand-in, not FFTW) behind the oracle rx loop"
+                          "unmodified src/fsk.c (oracle/_ref) on the %s, behind the oracle rx loop" % fft
                           if k == "reference" else "oracle port (two-bin direct DFT, no FFT): best-case CPU"),
-                      frames=total, seconds_per_pass=dt)
+                      frames=total, seconds_per_pass=dt,
+                      same_frames_as_first_arm=bool(sig == check))
     return out[kind], out[kind]["seconds_per_pass"], out
 
 

@@ -16,6 +16,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
 LIBORACLE = os.path.join(ORACLE_DIR, "liboracle.so")
 LIBREF = os.path.join(ORACLE_DIR, "_ref", "libfsk_ref.so")
+# the same unmodified src/fsk.c on MKL's DFTI FFT (oracle/shim/fftw3_dfti.c): timing only
+LIBREF_DFTI = os.path.join(ORACLE_DIR, "_ref", "libfsk_ref_dfti.so")
 REF_CLI = os.path.join(ORACLE_DIR, "_ref", "minimodem_ref")
 REF_CLI_TRACE = os.path.join(ORACLE_DIR, "_ref", "minimodem_ref_trace")
 REFERENCE_SRC = "/root/reference"
@@ -505,6 +507,31 @@ def ref():
     return _ref
 
 
+_ref_dfti = None
+
+
+def have_ref_dfti():
+    return os.path.exists(LIBREF_DFTI)
+
+
+def ref_dfti():
+    """oracle/_ref/libfsk_ref_dfti.so: needs PyTorch's libraries (MKL lives in libtorch_cpu.so)."""
+    global _ref_dfti
+    if _ref_dfti is None:
+        os.environ.setdefault("MKL_NUM_THREADS", "1")        # one transform per caller thread
+        import torch  # noqa: F401  (loads libtorch_cpu.so with its dependencies)
+        L = C.CDLL(LIBREF_DFTI)
+        fp = C.POINTER(C.c_float)
+        L.fsk_plan_new.argtypes = [C.c_float] * 4
+        L.fsk_plan_new.restype = C.c_void_p
+        L.fsk_plan_destroy.argtypes = [C.c_void_p]
+        L.fsk_find_frame.argtypes = [C.c_void_p, fp, C.c_uint, C.c_uint, C.c_uint, C.c_uint, C.c_float,
+                                     C.c_char_p, C.POINTER(C.c_ulonglong), fp, C.POINTER(C.c_uint)]
+        L.fsk_find_frame.restype = C.c_float
+        _ref_dfti = L
+    return _ref_dfti
+
+
 class RefPlan:
     """fsk_plan of the unmodified reference (src/fsk.c:33)."""
 
@@ -573,8 +600,8 @@ def rx_many(mode, samples, nsamples=None, nthreads=1, kind="port"):
     fps = np.zeros(nstreams, np.uint32)
     bx = np.zeros(nstreams, np.uint64)
     pn = ff = pd = None
-    if kind == "reference":
-        R = ref()
+    if kind in ("reference", "reference-dfti"):
+        R = ref() if kind == "reference" else ref_dfti()
         pn = C.cast(R.fsk_plan_new, C.c_void_p)
         ff = C.cast(R.fsk_find_frame, C.c_void_p)
         pd = C.cast(R.fsk_plan_destroy, C.c_void_p)

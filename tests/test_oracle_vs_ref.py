@@ -123,3 +123,45 @@ def test_find_frame_matches_compiled_reference_on_noisy_input(mode_name, kw):
                 assert sigma > 0, (mode_name, sigma, trial, got, want)
     assert n_found > n_checked // 8
     assert n_bad <= 1, n_bad      # razor-edge candidate flips only
+
+
+@pytest.mark.ref
+@pytest.mark.parametrize("mode,kw", [("1200", {}), ("300", {}), ("rtty", dict(sample_rate=8000)), ("same", {})])
+def test_dfti_backed_reference_build_agrees_with_the_portable_one(mode, kw):
+    """oracle/_ref/libfsk_ref_dfti.so (the unmodified src/fsk.c on MKL's FFT, used only to time the
+    reference fairly in bench.py) against oracle/_ref/libfsk_ref.so (the same source on the portable
+    FFT stand-in, which minted the golden vectors): same searches, same bits and frame starts,
+    confidences equal to FFT rounding."""
+    if not orc.have_ref_dfti():
+        pytest.skip("libfsk_ref_dfti.so not built (needs PyTorch's libtorch_cpu.so)")
+    import ctypes as C
+    m = orc.Mode(mode, **kw)
+    d = m.derived()
+    A, B = orc.ref(), orc.ref_dfti()
+    rng = np.random.default_rng(12)
+    a = orc.tx_words(m, rng.integers(0, 1 << m.n_data_bits, 40, dtype=np.uint32), 0.8, 4096, True)
+    a = (a + np.float32(0.05) * rng.standard_normal(a.size).astype(np.float32)).astype(np.float32)
+    a = np.concatenate([a, np.zeros(4 * d.expect_nsamples, np.float32)])
+    pa = A.fsk_plan_new(m.sample_rate, m.mark_f, m.space_f, m.band_width)
+    pb = B.fsk_plan_new(m.sample_rate, m.mark_f, m.space_f, m.band_width)
+    assert pa and pb
+    try_max = int(d.nsamples_per_bit) + d.nsamples_overscan
+    n_checked = 0
+    for pos in range(0, a.size - 3 * d.expect_nsamples, max(1, d.expect_nsamples // 3)):
+        w = np.ascontiguousarray(a[pos:pos + 3 * d.expect_nsamples])
+        res = []
+        for L, p in ((A, pa), (B, pb)):
+            bits, ampl, start = C.c_ulonglong(0), C.c_float(0), C.c_uint(0)
+            c = L.fsk_find_frame(p, orc.fptr(w), d.expect_nsamples, 0, try_max, max(1, try_max // 8),
+                                 float("inf"), d.expect_data, C.byref(bits), C.byref(ampl), C.byref(start))
+            res.append((np.float32(c), bits.value, np.float32(ampl.value), start.value))
+        (ca, ba, aa, sa), (cb, bb, ab, sb) = res
+        if ba == bb and sa == sb:
+            assert gu.close(ca, cb, 1e-4, cond=gu.CONF_COND) and gu.close(aa, ab)
+            n_checked += 1
+        else:
+            # two float FFTs may prefer different candidates only when those are equal to rounding
+            assert gu.close(ca, cb, 1e-3, cond=gu.CONF_COND), (pos, res)
+    assert n_checked > 20
+    A.fsk_plan_destroy(pa)
+    B.fsk_plan_destroy(pb)
