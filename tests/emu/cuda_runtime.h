@@ -19,7 +19,8 @@
  *   - cp.async: copies are queued per lane and land when that lane executes the matching
  *     wait_group (FSK_EMU_ASYNC=late, the default: a missing wait reads stale data) or at once
  *     (FSK_EMU_ASYNC=eager: a copy issued while its target is still being read corrupts it);
- *   - sqrt.approx / div.approx as IEEE sqrtf and division (the GPU's are <= 2 ulp away).
+ *   - sqrt.approx / div.approx as IEEE sqrtf and division (the GPU's are <= 2 ulp away);
+ *     FSK_EMU_ULP=n perturbs both by up to n ulp to show that no test hinges on their rounding.
  * What it does not: timing, bank conflicts, memory coalescing, the TMA/mbarrier variant.
  */
 #ifndef FSK_EMU_CUDA_RUNTIME_H
@@ -277,8 +278,31 @@ static inline size_t __cvta_generic_to_shared(const void *p)
 static inline void *__cvta_shared_to_generic(size_t a) { return emu::blk->smem + a; }
 
 /* the inline-PTX wrappers of fsk_b200_device.cuh (guarded there by FSK_EMU) */
-static inline float fast_sqrt(float x) { return sqrtf(x); }
-static inline float fast_div(float a, float b) { return a / b; }
+/* FSK_EMU_ULP=n: perturb the two approximate units by up to n ulp (pseudo-randomly, either way), to
+ * see that no test hinges on their exact rounding -- the B200's sqrt.approx / div.approx are within
+ * 2 ulp of these */
+namespace emu {
+extern int approx_ulp;
+static inline float jitter(float v)
+{
+    if (approx_ulp <= 0 || !std::isfinite(v) || v == 0.0f)
+	return v;
+    /* a fixed function of the value, like a hardware unit: the same operand gives the same result */
+    int32_t bits;
+    memcpy(&bits, &v, 4);
+    uint32_t h = (uint32_t)bits * 2654435761u;
+    h ^= h >> 15;
+    h *= 2246822519u;
+    h ^= h >> 13;
+    const int k = (int)(h % (2u * (unsigned)approx_ulp + 1u)) - approx_ulp;
+    bits += v > 0 ? k : -k;
+    float r;
+    memcpy(&r, &bits, 4);
+    return std::isfinite(r) ? r : v;
+}
+}
+static inline float fast_sqrt(float x) { return emu::jitter(sqrtf(x)); }
+static inline float fast_div(float a, float b) { return emu::jitter(a / b); }
 static inline void cp_async_commit() { emu::cp_async_commit_group(); }
 template <int NKEEP>
 static inline void cp_async_wait() { emu::cp_async_wait_group(NKEEP); }

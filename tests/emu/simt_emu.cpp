@@ -10,6 +10,7 @@ namespace emu {
 
 thread_local Block *blk = NULL;
 int async_eager = 0;
+int approx_ulp = 0;
 
 [[noreturn]] void die(const char *what)
 {
@@ -141,6 +142,7 @@ void run_grid(unsigned grid, unsigned block, size_t smem, const void *body, void
 	return;
     const char *e = getenv("FSK_EMU_ASYNC");
     async_eager = e && strcmp(e, "eager") == 0;
+    approx_ulp = (e = getenv("FSK_EMU_ULP")) ? atoi(e) : 0;
     unsigned nthreads = std::thread::hardware_concurrency();
     if ((e = getenv("FSK_EMU_THREADS")))
 	nthreads = (unsigned)atoi(e);
