@@ -106,6 +106,8 @@ EXPORTS = [
 ]
 
 _lib = None
+# set by tests/emu/emu_mode.py only: lets the parity tests run against the host emulation build
+ALLOW_NON_PRODUCT_LIBRARY = False
 
 
 def build(force=False):
@@ -126,6 +128,12 @@ def lib():
         raise RuntimeError("%s is missing: build it with minimodem_b200.build() "
                            "(make -C minimodem_b200/csrc); there is no CPU/PyTorch fallback" % LIB_PATH)
     L = C.CDLL(LIB_PATH)
+    L.fsk_b200_version.restype = C.c_char_p
+    if b"sm_100a" not in L.fsk_b200_version() and not ALLOW_NON_PRODUCT_LIBRARY:
+        # FSK_B200_LIB exists for tuning builds of the CUDA library; anything else (the tests' host
+        # emulation of the kernels, tests/emu) must never stand in for it silently
+        raise RuntimeError("%s is not a build of the sm_100a library (%s); the binding refuses it"
+                           % (LIB_PATH, L.fsk_b200_version().decode()))
     fp, u32p = C.POINTER(C.c_float), C.c_void_p
     L.fsk_plan_new.argtypes = [C.c_float] * 4
     L.fsk_plan_new.restype = C.POINTER(FskPlanStruct)

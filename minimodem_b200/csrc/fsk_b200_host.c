@@ -37,7 +37,11 @@ void fsk_b200_set_error(const char *fmt, ...)
 }
 
 const char *fsk_b200_last_error(void) { return last_error; }
+#ifdef FSK_EMU	/* tests/emu: the kernels' source on the host SIMT emulator; never the product */
+const char *fsk_b200_version(void) { return "fsk_b200 0.1 HOST-EMULATION (tests only)"; }
+#else
 const char *fsk_b200_version(void) { return "fsk_b200 0.1 sm_100a"; }
+#endif
 unsigned long long fsk_b200_launch_count(void) { return fsk_b200_cuda_launch_count(); }
 
 /* ------------------------------------------------------------------------ */

@@ -36,6 +36,7 @@ def activate():
     import torch
     import minimodem_b200.api as api
     assert api.LIB_PATH == LIB, "minimodem_b200 was imported before the emulation was selected"
+    api.ALLOW_NON_PRODUCT_LIBRARY = True      # the binding refuses the emulation build otherwise
     # host memory plays device memory
     torch.Tensor.is_cuda = property(lambda self: True)
     torch.cuda.synchronize = lambda *a, **k: None

@@ -128,3 +128,16 @@ def test_no_cpu_fallback_without_a_device():
         mm.RxEngine(p)
     with pytest.raises(ValueError):
         mm.FskPlan(48000, 1200, 2200, 200)
+
+
+def test_binding_refuses_the_emulation_build():
+    """tests/emu builds the kernels' source for a host SIMT emulator behind the same C ABI; it is
+    test infrastructure, and the product binding must not accept it in the library's place."""
+    import subprocess
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+    import emu_mode
+    lib = emu_mode.build()
+    r = subprocess.run([sys.executable, "-c", "import minimodem_b200 as mm; mm.lib()"], cwd=ROOT,
+                       env=dict(os.environ, FSK_B200_LIB=lib), stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    assert r.returncode != 0 and b"HOST-EMULATION" in r.stdout and b"refuses" in r.stdout
