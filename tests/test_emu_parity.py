@@ -44,3 +44,23 @@ def test_random_modes_and_dropouts_on_the_emulated_kernels():
     emulated kernels -> records equal to the oracle's rx loop."""
     tail = run_emulated("random_mode or dropouts", "late", 1200, module="emu_fuzz.py")
     assert "88 passed" in tail
+
+
+def test_the_emulator_itself():
+    """tests/emu/selftest.cpp: hand-verifiable kernels.  Group-masked shuffles / votes with
+    divergent trip counts, block barriers and dynamic shared memory give CUDA's results; cp.async
+    data is invisible before the issuing thread's wait in `late` mode and visible at once in
+    `eager` mode; a lane missing from a *_sync, a lane outside its own mask, a copy past the
+    shared-memory allocation and a thread that exits with copies in flight are all reported."""
+    emu = os.path.join(ROOT, "tests", "emu")
+    subprocess.check_call(["make", "-s", "-C", emu, "selftest"])
+    exe = os.path.join(emu, "build", "selftest")
+    for case in ("groups", "block", "async"):
+        for mode in ("late", "eager"):
+            r = subprocess.run([exe, case], env=dict(os.environ, FSK_EMU_ASYNC=mode), stdout=subprocess.PIPE,
+                               stderr=subprocess.STDOUT, timeout=120)
+            assert r.returncode == 0 and b"ok" in r.stdout, (case, mode, r.stdout[-400:])
+    for case, msg in (("deadlock", b"deadlock"), ("wrong_mask", b"mask does not name it"),
+                      ("oob", b"outside the block's shared memory"), ("exit_in_flight", b"copies in flight")):
+        r = subprocess.run([exe, case], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=120)
+        assert r.returncode != 0 and msg in r.stdout, (case, r.returncode, r.stdout[-400:])
