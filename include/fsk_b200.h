@@ -236,6 +236,31 @@ int fsk_b200_rx_batch_host(fsk_b200_engine *e, const float *host_samples, size_t
 	fsk_b200_frame *host_frames, uint32_t max_frames,
 	fsk_b200_stream_state *host_states);
 
+/* Live streams.  fsk_b200_rx_batch works on whatever each row holds; a receiver that is fed in
+ * chunks keeps, per stream, the samples the loop has not consumed yet and appends the new ones:
+ *
+ *   fsk_b200_engine_set_holdback(e, fsk_b200_stream_window(p));   // once
+ *   for every chunk:
+ *       fsk_b200_stream_push(d_rows, n, stride, d_fill, d_states, d_chunk, chunk_stride, d_chunk_len, 0, NULL, st);
+ *       fsk_b200_rx_batch(e, d_rows, n, stride, d_fill, 0, d_frames, max_frames, d_states, st);
+ *       ... consume states[s].nframes records of each stream ...
+ *   at the end of a stream: fsk_b200_engine_set_holdback(e, 0) and one more rx_batch (the reference's
+ *   end-of-input rule: it analyses what is left as long as expect_nsamples remain, src/minimodem.c:1229)
+ *
+ * With the holdback at fsk_b200_stream_window() a search starts only when every sample it can touch
+ * has arrived, so the records do not depend on how the stream was cut into chunks.
+ *
+ * fsk_b200_stream_push: per stream s, the unconsumed tail [states[s].pos, fill[s]) of row s moves to
+ * the front, chunk_len[s] (or chunk_len_all when chunk_len is NULL) floats of chunk row s are
+ * appended (what does not fit in `stride` is dropped and counted in dropped[s], if given),
+ * fill[s] becomes the new length, and the state is set to pos = 0, nframes = 0, done = 0 with the
+ * carrier/squelch/session fields untouched.  All pointers are device memory. */
+uint32_t fsk_b200_stream_window(const fsk_b200_rx_params *p);
+int fsk_b200_engine_set_holdback(fsk_b200_engine *e, uint32_t nsamples);
+int fsk_b200_stream_push(float *samples, size_t nstreams, size_t stride, uint32_t *fill,
+	fsk_b200_stream_state *states, const float *chunk, size_t chunk_stride, const uint32_t *chunk_len,
+	uint32_t chunk_len_all, uint32_t *dropped, void *stream);
+
 /* N3, batched -- fsk_detect_carrier (src/fsk.c:543-581, the --auto-carrier probe of
  * src/minimodem.c:1179-1220) for many streams in one launch: stream s is analysed over the
  * nsamples (1..fftsize) floats at samples[s*stride + offset[s]] (offset may be NULL = 0), zero

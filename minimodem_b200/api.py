@@ -102,6 +102,7 @@ EXPORTS = [
     "fsk_b200_s16_to_f32", "fsk_b200_rx_batch_host_s16", "fsk_b200_decode_ascii_batch",
     "fsk_b200_decode_batch", "fsk_b200_decoder_for_mode", "fsk_b200_decode_max_bytes_per_frame",
     "fsk_b200_decode_max_bytes", "fsk_b200_detect_carrier_batch",
+    "fsk_b200_stream_window", "fsk_b200_engine_set_holdback", "fsk_b200_stream_push",
     "fsk_b200_version", "fsk_b200_launch_count", "fsk_b200_last_error",
 ]
 
@@ -195,6 +196,13 @@ def lib():
     L.fsk_b200_detect_carrier_batch.argtypes = [C.c_int, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p,
                                                 C.c_uint32, C.c_float, C.c_void_p, C.c_void_p]
     L.fsk_b200_detect_carrier_batch.restype = C.c_int
+    L.fsk_b200_stream_window.argtypes = [C.POINTER(RxParams)]
+    L.fsk_b200_stream_window.restype = C.c_uint32
+    L.fsk_b200_engine_set_holdback.argtypes = [C.c_void_p, C.c_uint32]
+    L.fsk_b200_engine_set_holdback.restype = C.c_int
+    L.fsk_b200_stream_push.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_size_t, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+    L.fsk_b200_stream_push.restype = C.c_int
     L.fsk_b200_sin_table.argtypes = [C.POINTER(C.c_float), C.c_uint, C.c_float]
     L.fsk_b200_sin_table.restype = None
     L.fsk_b200_version.restype = C.c_char_p
@@ -439,6 +447,17 @@ class RxEngine:
             _err("fsk_b200_decode_ascii_batch", rc)
         return out, cnt
 
+    def stream_window(self):
+        """fsk_b200_stream_window: the farthest sample a search can touch from its start."""
+        return int(lib().fsk_b200_stream_window(C.byref(self.params)))
+
+    def set_holdback(self, nsamples):
+        """fsk_b200_engine_set_holdback: searches start only with this many samples left (0 = the
+        reference's end-of-input rule)."""
+        rc = lib().fsk_b200_engine_set_holdback(self._e, int(nsamples))
+        if rc:
+            _err("fsk_b200_engine_set_holdback", rc)
+
     def decode_batch(self, kind, frames, states, dstates=None, out_stride=None, stream=None):
         """Device-side databits decode (N1) of the records of rx_batch with decoder `kind`
         (DECODE_*): CUDA tensors in, (bytes [nstreams, out_stride] uint8, counts [nstreams] int32)
@@ -508,6 +527,18 @@ def detect_carrier_batch(fftsize, samples, nsamples, min_mag_threshold, offset=N
     if rc:
         _err("fsk_b200_detect_carrier_batch", rc)
     return out
+
+
+def stream_push(rows, fill, states, chunk, chunk_len=None, dropped=None, stream=None):
+    """fsk_b200_stream_push on CUDA tensors: rows [n, stride] float32, fill [n] int32 (in/out), states
+    [n, STATE_WORDS] int32 (in/out), chunk [n, chunk_stride] float32, chunk_len [n] int32 or an int."""
+    n, stride = rows.shape
+    per = chunk_len if hasattr(chunk_len, "data_ptr") else None
+    common = 0 if per is not None else int(chunk.shape[1] if chunk_len is None else chunk_len)
+    rc = lib().fsk_b200_stream_push(_ptr(rows), n, stride, _ptr(fill), _ptr(states), _ptr(chunk),
+                                    chunk.shape[1], _ptr(per), common, _ptr(dropped), _stream_handle(stream))
+    if rc:
+        _err("fsk_b200_stream_push", rc)
 
 
 def decode_max_bytes(kind, n_data_bits, nframes):

@@ -451,6 +451,47 @@ int fsk_b200_rx_batch(fsk_b200_engine *e, const float *samples, size_t nstreams,
 	    nsamples, nsamples_all, frames, max_frames, states, stream);
 }
 
+/* ---- live streams ------------------------------------------------------------ */
+
+uint32_t fsk_b200_stream_window(const fsk_b200_rx_params *p)
+{
+    /* the farthest sample a search that starts at `pos` can touch: its last candidate plus the span
+     * of the frame's bit windows (src/fsk.c:481, :204) */
+    return p ? p->try_max_nocarrier - 1u + p->span_nsamples : 0u;
+}
+
+int fsk_b200_engine_set_holdback(fsk_b200_engine *e, uint32_t nsamples)
+{
+    if (!e) {
+	fsk_b200_set_error("set_holdback: NULL engine");
+	return -EINVAL;
+    }
+    /* the loop's own stop rule (src/minimodem.c:1229) is the floor */
+    e->loopc.expect_nsamples = nsamples > e->params.expect_nsamples ? nsamples : e->params.expect_nsamples;
+    return 0;
+}
+
+int fsk_b200_stream_push(float *samples, size_t nstreams, size_t stride, uint32_t *fill,
+	fsk_b200_stream_state *states, const float *chunk, size_t chunk_stride, const uint32_t *chunk_len,
+	uint32_t chunk_len_all, uint32_t *dropped, void *stream)
+{
+    if (nstreams == 0)
+	return 0;
+    int rc = check_layout(samples, stride);
+    if (rc)
+	return rc;
+    if (!fill || !states || (!chunk && (chunk_len || chunk_len_all))) {
+	fsk_b200_set_error("stream_push: NULL argument");
+	return -EINVAL;
+    }
+    if (!fsk_b200_cuda_device_ok()) {
+	fsk_b200_set_error("no usable CUDA device (there is no CPU fallback)");
+	return -ENODEV;
+    }
+    return fsk_b200_cuda_stream_push(samples, nstreams, stride, fill, states, chunk, chunk_stride, chunk_len,
+	    chunk_len_all, dropped, stream);
+}
+
 int fsk_b200_rx_batch_host(fsk_b200_engine *e, const float *host_samples, size_t nstreams,
 	size_t stride, uint32_t nsamples_all, fsk_b200_frame *host_frames, uint32_t max_frames,
 	fsk_b200_stream_state *host_states)

@@ -66,6 +66,9 @@ int  fsk_b200_cuda_band_mags(void *ce, int fftsize, const float *host_samples,
 	unsigned int nsamples, unsigned int nbands, float *host_mags);
 int  fsk_b200_cuda_detect_carrier_batch(int fftsize, const float *samples, size_t nstreams, size_t stride,
 	const uint32_t *offset, uint32_t nsamples, float min_mag_threshold, int32_t *out_band, void *stream);
+int  fsk_b200_cuda_stream_push(float *samples, size_t nstreams, size_t stride, uint32_t *fill,
+	fsk_b200_stream_state *states, const float *chunk, size_t chunk_stride, const uint32_t *chunk_len,
+	uint32_t chunk_len_all, uint32_t *dropped, void *stream);
 int  fsk_b200_cuda_tx_batch(const fsk_b200_tx_config *cfg, const float *sin_table,
 	uint32_t table_len, const uint32_t *words, uint32_t nwords, const uint32_t *lead_in,
 	float *samples_out, size_t nstreams, size_t stride, uint32_t nsamples_out, void *stream);

@@ -929,6 +929,52 @@ __global__ void k_s16_to_f32_scalar(const short *__restrict__ src, float *__rest
 }
 
 /* ------------------------------------------------------------------------ */
+/* live streams: between two rx launches, each stream's unconsumed tail moves to */
+/* the front of its row and the new samples are appended (one warp per stream)   */
+/* ------------------------------------------------------------------------ */
+__global__ void k_stream_push(float *__restrict__ samples, unsigned nstreams, size_t stride,
+	uint32_t *__restrict__ fill, fsk_b200_stream_state *__restrict__ states,
+	const float *__restrict__ chunk, size_t chunk_stride, const uint32_t *__restrict__ chunk_len,
+	uint32_t chunk_len_all, uint32_t *__restrict__ dropped)
+{
+    const unsigned lane = threadIdx.x & 31;
+    const unsigned s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (s >= nstreams)
+	return;						/* whole warps leave together */
+    float *row = samples + (size_t)s * stride;
+    const unsigned have = fill[s];
+    unsigned long long pos64 = states[s].pos;
+    const unsigned pos = pos64 < have ? (unsigned)pos64 : have;
+    const unsigned tail = have - pos;
+    /* forward move in tiles of 32: a tile is read completely before it is written, and the
+     * destination of tile k ends below the source of tile k+1 (dst = src - pos, pos >= 0) */
+    if (pos)
+	for (unsigned k = 0; k < tail; k += 32) {
+	    const float v = k + lane < tail ? row[pos + k + lane] : 0.f;
+	    __syncwarp();
+	    if (k + lane < tail)
+		row[k + lane] = v;
+	    __syncwarp();
+	}
+    unsigned len = chunk_len ? chunk_len[s] : chunk_len_all;
+    const unsigned room = (unsigned)min((size_t)0xffffffffu, stride) - tail;
+    const unsigned drop = len > room ? len - room : 0u;
+    len -= drop;
+    const float *src = chunk + (size_t)s * chunk_stride;
+    for (unsigned i = lane; i < len; i += 32)
+	row[tail + i] = src[i];
+    __syncwarp();		/* every lane has read fill[s] and states[s] before lane 0 rewrites them */
+    if (lane == 0) {
+	fill[s] = tail + len;
+	states[s].pos = 0;
+	states[s].nframes = 0;				/* the record buffer starts over */
+	states[s].done = 0;
+	if (dropped)
+	    dropped[s] = drop;
+    }
+}
+
+/* ------------------------------------------------------------------------ */
 /* N1: frame records -> bytes through one of the reference's databits decoders  */
 /* (fsk_b200_decode_core.h) behind the bit chop of src/minimodem.c:1415-1446;   */
 /* one thread per stream, the decoder state of the stream in registers/local    */
@@ -1500,6 +1546,25 @@ extern "C" int fsk_b200_cuda_s16_to_f32(const int16_t *src, float *dst, size_t n
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
 	fsk_b200_set_error("s16_to_f32 launch: %s", cudaGetErrorString(e));
+	return -EIO;
+    }
+    return 0;
+}
+
+extern "C" int fsk_b200_cuda_stream_push(float *samples, size_t nstreams, size_t stride, uint32_t *fill,
+	fsk_b200_stream_state *states, const float *chunk, size_t chunk_stride, const uint32_t *chunk_len,
+	uint32_t chunk_len_all, uint32_t *dropped, void *stream)
+{
+    if (nstreams == 0)
+	return 0;
+    const unsigned threads = 128;
+    const size_t blocks = (nstreams * 32 + threads - 1) / threads;
+    FSK_LAUNCH(k_stream_push, (unsigned)blocks, threads, 0, (cudaStream_t)stream, samples, (unsigned)nstreams,
+	    stride, fill, states, chunk, chunk_stride, chunk_len, chunk_len_all, dropped);
+    g_launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+	fsk_b200_set_error("stream_push launch: %s", cudaGetErrorString(e));
 	return -EIO;
     }
     return 0;

@@ -876,3 +876,83 @@ def test_batched_entry_points_reject_bad_arguments():
     assert L.fsk_b200_last_error()
     assert mm.launch_count() == before
     assert L.fsk_b200_rx_batch(eng._e, p(x), 0, 4096, None, 4096, p(fr), 16, p(st), None) == 0   # empty batch
+
+
+# --------------------------------------------------------------------------
+# live streams: chunked feeding with carry-over == one pass over the whole stream
+# --------------------------------------------------------------------------
+@pytest.mark.parametrize("mode,kw", [("1200", {}), ("300", {}), ("rtty", dict(sample_rate=8000)), ("same", {})])
+def test_streams_fed_in_chunks_give_the_records_of_one_pass(mode, kw):
+    """fsk_b200_stream_push + fsk_b200_engine_set_holdback: every stream gets its samples in chunks of
+    its own random sizes (down to a handful of samples), keeps what the loop has not consumed, and is
+    flushed at the end with the reference's end-of-input rule.  The concatenated records must be
+    those of a single pass over the complete stream -- identical, not merely close: the same kernel
+    sees the same samples in the same windows."""
+    rx = orc.Mode(mode, **kw)
+    d = rx.derived()
+    rng = np.random.default_rng(31)
+    nstreams = 6
+    full = []
+    for s in range(nstreams):
+        parts = [np.zeros(int(rng.integers(0, 3 * int(d.nsamples_per_bit))), np.float32)]
+        for _ in range(int(rng.integers(1, 4))):
+            w = rng.integers(0, 1 << rx.n_data_bits, int(rng.integers(3, 14)), dtype=np.uint64).astype(np.uint32)
+            parts.append(orc.tx_words(rx, w, float(rng.uniform(0.3, 1.0)), 4096, True))
+            parts.append(np.zeros(int(rng.integers(0, 40)) * int(d.nsamples_per_bit), np.float32))
+        x = np.concatenate(parts).astype(np.float32)
+        full.append((x + np.float32(0.004) * rng.standard_normal(x.size).astype(np.float32)).astype(np.float32))
+    eng, _ = engine_for((mode, kw))
+    # one pass
+    want, st_want = rx_on_gpu(eng, full)
+    # chunked
+    window = eng.stream_window()
+    assert window == eng.params.try_max_nocarrier - 1 + eng.params.span_nsamples
+    max_chunk = 3 * window
+    stride = pad4(window + 2 * max_chunk + 64)
+    rows = torch.zeros((nstreams, stride), dtype=torch.float32, device=dev())
+    fill = torch.zeros((nstreams,), dtype=torch.int32, device=dev())
+    states = torch.zeros((nstreams, mm.STATE_WORDS), dtype=torch.int32, device=dev())
+    dropped = torch.zeros((nstreams,), dtype=torch.int32, device=dev())
+    eng.set_holdback(window)
+    fed = [0] * nstreams
+    got = [[] for _ in range(nstreams)]
+    max_frames = eng.max_frames(stride)
+
+    def collect(frames, st):
+        fr, s1 = mm.frames_to_numpy(frames), mm.states_to_numpy(st)
+        for i in range(nstreams):
+            got[i].extend(fr[i, :s1["nframes"][i]].copy())
+        return s1
+
+    for _ in range(10000):
+        if all(fed[i] >= len(full[i]) for i in range(nstreams)):
+            break
+        chunk = np.zeros((nstreams, max_chunk), np.float32)
+        clen = np.zeros(nstreams, np.int32)
+        for i in range(nstreams):
+            k = int(min(rng.integers(1, max_chunk + 1) if rng.random() < 0.8 else rng.integers(1, 9),
+                        len(full[i]) - fed[i]))
+            chunk[i, :k] = full[i][fed[i]:fed[i] + k]
+            clen[i] = k
+            fed[i] += k
+        mm.stream_push(rows, fill, states, torch.from_numpy(chunk).to(dev()), torch.from_numpy(clen).to(dev()),
+                       dropped=dropped)
+        frames, states = eng.rx_batch(rows, nsamples=stride, nsamples_each=fill, max_frames=max_frames, states=states)
+        torch.cuda.synchronize()
+        assert int(dropped.sum()) == 0
+        collect(frames, states)
+    else:
+        raise AssertionError("feeding did not finish")
+    # end of input: the reference's rule takes over (src/minimodem.c:1229)
+    eng.set_holdback(0)
+    mm.stream_push(rows, fill, states, torch.zeros((nstreams, 4), dtype=torch.float32, device=dev()), 0)
+    frames, states = eng.rx_batch(rows, nsamples=stride, nsamples_each=fill, max_frames=max_frames, states=states)
+    torch.cuda.synchronize()
+    s_end = collect(frames, states)
+    assert (s_end["done"] == 1).all()
+    for i in range(nstreams):
+        a = np.array(got[i], dtype=mm.FRAME_DTYPE) if got[i] else np.zeros(0, mm.FRAME_DTYPE)
+        assert np.array_equal(a, want[i]), (mode, i, len(a), len(want[i]))
+    for key in ("carrier", "carrier_nsamples", "nframes_decoded", "confidence_total", "amplitude_total",
+                "noconfidence", "track_amplitude", "peak_confidence"):
+        assert np.array_equal(s_end[key], st_want[key]), key
