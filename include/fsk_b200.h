@@ -276,6 +276,15 @@ int fsk_b200_detect_carrier_batch(int fftsize, const float *samples, size_t nstr
  * fsk_b200_rx_batch_host_s16: like fsk_b200_rx_batch_host, but the host streams are int16 --
  * half the bytes cross PCIe, the widening happens on the device. */
 int fsk_b200_s16_to_f32(const int16_t *src, float *dst, size_t nstreams, size_t stride, void *stream);
+
+/* N2, the file side: where the samples of a RIFF/WAVE image are (the container the reference's
+ * tests and its default `--file` output use; the reference itself goes through libsndfile,
+ * src/simpleaudio-sndfile.c:88-160).  Mono PCM16 (format 1) and IEEE float32 (format 3) only, which
+ * is what its transmitter writes (src/minimodem.c:533, --float-samples).  Host memory.  Returns 0 and
+ * fills data_offset (bytes from the start of the image), nsamples, sample_rate and is_float, or
+ * -EINVAL for anything else (truncated data chunks are clipped to the image). */
+int fsk_b200_wav_locate(const void *image, size_t nbytes, size_t *data_offset, size_t *nsamples,
+	uint32_t *sample_rate, int *is_float);
 int fsk_b200_rx_batch_host_s16(fsk_b200_engine *e, const int16_t *host_samples, size_t nstreams,
 	size_t stride, uint32_t nsamples_all,
 	fsk_b200_frame *host_frames, uint32_t max_frames,

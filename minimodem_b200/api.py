@@ -102,7 +102,7 @@ EXPORTS = [
     "fsk_b200_s16_to_f32", "fsk_b200_rx_batch_host_s16", "fsk_b200_decode_ascii_batch",
     "fsk_b200_decode_batch", "fsk_b200_decoder_for_mode", "fsk_b200_decode_max_bytes_per_frame",
     "fsk_b200_decode_max_bytes", "fsk_b200_detect_carrier_batch",
-    "fsk_b200_stream_window", "fsk_b200_engine_set_holdback", "fsk_b200_stream_push",
+    "fsk_b200_stream_window", "fsk_b200_engine_set_holdback", "fsk_b200_stream_push", "fsk_b200_wav_locate",
     "fsk_b200_version", "fsk_b200_launch_count", "fsk_b200_last_error",
 ]
 
@@ -203,6 +203,9 @@ def lib():
     L.fsk_b200_stream_push.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,
                                        C.c_size_t, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
     L.fsk_b200_stream_push.restype = C.c_int
+    L.fsk_b200_wav_locate.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t),
+                                      C.POINTER(C.c_uint32), C.POINTER(C.c_int)]
+    L.fsk_b200_wav_locate.restype = C.c_int
     L.fsk_b200_sin_table.argtypes = [C.POINTER(C.c_float), C.c_uint, C.c_float]
     L.fsk_b200_sin_table.restype = None
     L.fsk_b200_version.restype = C.c_char_p
@@ -539,6 +542,15 @@ def stream_push(rows, fill, states, chunk, chunk_len=None, dropped=None, stream=
                                     chunk.shape[1], _ptr(per), common, _ptr(dropped), _stream_handle(stream))
     if rc:
         _err("fsk_b200_stream_push", rc)
+
+
+def wav_locate(image):
+    """fsk_b200_wav_locate on a bytes object: (data_offset, nsamples, sample_rate, is_float)."""
+    off, n, rate, isf = C.c_size_t(0), C.c_size_t(0), C.c_uint32(0), C.c_int(0)
+    rc = lib().fsk_b200_wav_locate(image, len(image), C.byref(off), C.byref(n), C.byref(rate), C.byref(isf))
+    if rc:
+        _err("fsk_b200_wav_locate", rc)
+    return off.value, n.value, rate.value, bool(isf.value)
 
 
 def decode_max_bytes(kind, n_data_bits, nframes):

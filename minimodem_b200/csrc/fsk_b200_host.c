@@ -515,6 +515,50 @@ int fsk_b200_s16_to_f32(const int16_t *src, float *dst, size_t nstreams, size_t 
     return fsk_b200_cuda_s16_to_f32(src, dst, nstreams, stride, stream);
 }
 
+static uint32_t rd_u32le(const unsigned char *p) { return p[0] | p[1] << 8 | p[2] << 16 | (uint32_t)p[3] << 24; }
+static uint32_t rd_u16le(const unsigned char *p) { return p[0] | p[1] << 8; }
+
+int fsk_b200_wav_locate(const void *image, size_t nbytes, size_t *data_offset, size_t *nsamples,
+	uint32_t *sample_rate, int *is_float)
+{
+    const unsigned char *b = image;
+    if (!b || !data_offset || !nsamples || !sample_rate || !is_float || nbytes < 12
+	    || memcmp(b, "RIFF", 4) != 0 || memcmp(b + 8, "WAVE", 4) != 0) {
+	fsk_b200_set_error("wav_locate: not a RIFF/WAVE image");
+	return -EINVAL;
+    }
+    size_t pos = 12;
+    int have_fmt = 0;
+    unsigned fmt = 0, channels = 0, bits = 0;
+    while (pos + 8 <= nbytes) {
+	const uint32_t len = rd_u32le(b + pos + 4);
+	const unsigned char *body = b + pos + 8;
+	if (memcmp(b + pos, "fmt ", 4) == 0 && len >= 16 && pos + 8 + 16 <= nbytes) {
+	    fmt = rd_u16le(body);
+	    channels = rd_u16le(body + 2);
+	    *sample_rate = rd_u32le(body + 4);
+	    bits = rd_u16le(body + 14);
+	    have_fmt = 1;
+	} else if (memcmp(b + pos, "data", 4) == 0) {
+	    if (!have_fmt || channels != 1 || !((fmt == 1 && bits == 16) || (fmt == 3 && bits == 32))) {
+		fsk_b200_set_error("wav_locate: only mono PCM16 and float32 are supported (format %u, %u channels, %u bits)",
+			fmt, channels, bits);
+		return -EINVAL;
+	    }
+	    size_t n = len;
+	    if (n > nbytes - (pos + 8))
+		n = nbytes - (pos + 8);		/* a writer that died before patching the header */
+	    *data_offset = pos + 8;
+	    *is_float = fmt == 3;
+	    *nsamples = n / (bits / 8);
+	    return 0;
+	}
+	pos += 8 + (size_t)len + (len & 1);
+    }
+    fsk_b200_set_error("wav_locate: no data chunk");
+    return -EINVAL;
+}
+
 int fsk_b200_rx_batch_host_s16(fsk_b200_engine *e, const int16_t *host_samples, size_t nstreams,
 	size_t stride, uint32_t nsamples_all, fsk_b200_frame *host_frames, uint32_t max_frames,
 	fsk_b200_stream_state *host_states)

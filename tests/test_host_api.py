@@ -141,3 +141,37 @@ def test_binding_refuses_the_emulation_build():
     r = subprocess.run([sys.executable, "-c", "import minimodem_b200 as mm; mm.lib()"], cwd=ROOT,
                        env=dict(os.environ, FSK_B200_LIB=lib), stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
     assert r.returncode != 0 and b"HOST-EMULATION" in r.stdout and b"refuses" in r.stdout
+
+
+def test_wav_locate_on_the_reference_transmitters_files(tmp_path):
+    """N2, the file side: the WAV images the reference's own transmitter writes (S16 by default,
+    float32 with --float-samples) are located exactly; what is not mono PCM16/float32 is refused."""
+    import struct
+    import subprocess
+    import golden_util as gu
+    g = gu.load("small-1200")
+    a = gu.audio(refcases.BY_NAME["small-1200"], g)
+
+    def wav(samples, rate, fmt, bits, channels=1, junk=b""):
+        data = samples.astype("<f4").tobytes() if fmt == 3 else np.round(samples * 32768).astype("<i2").tobytes()
+        body = b"WAVE" + junk + b"fmt " + struct.pack("<IHHIIHH", 16, fmt, channels, rate, rate * bits // 8 * channels,
+                                                      bits // 8 * channels, bits) + b"data" + struct.pack("<I", len(data)) + data
+        return b"RIFF" + struct.pack("<I", len(body)) + body
+
+    off, n, rate, isf = mm.wav_locate(wav(a, 48000, 1, 16))
+    assert (off, n, rate, isf) == (44, a.size, 48000, False)
+    off, n, rate, isf = mm.wav_locate(wav(a, 8000, 3, 32, junk=b"LIST" + struct.pack("<I", 5) + b"abcde\0"))
+    assert (n, rate, isf) == (a.size, 8000, True) and off == 44 + 14
+    img = wav(a, 48000, 1, 16)
+    off, n, _, _ = mm.wav_locate(img[:44 + 100])              # truncated file: clipped, not refused
+    assert (off, n) == (44, 50)
+    for bad in (b"", b"RIFFxxxxWAVX", wav(a, 48000, 1, 16, channels=2), wav(a, 48000, 1, 8), img[:30]):
+        with pytest.raises(RuntimeError):
+            mm.wav_locate(bad)
+    if orc.have_ref():                                         # a file written by the unmodified reference CLI
+        for extra, isfloat in (([], False), (["--float-samples"], True)):
+            path = str(tmp_path / "t.wav")
+            subprocess.run([orc.REF_CLI, "--tx", "--file", path, "1200"] + extra, input=b"wav header\n", check=True)
+            image = open(path, "rb").read()
+            off, n, rate, isf = mm.wav_locate(image)
+            assert rate == 48000 and isf == isfloat and off + n * (4 if isfloat else 2) == len(image)
