@@ -956,3 +956,45 @@ def test_streams_fed_in_chunks_give_the_records_of_one_pass(mode, kw):
     for key in ("carrier", "carrier_nsamples", "nframes_decoded", "confidence_total", "amplitude_total",
                 "noconfidence", "track_amplitude", "peak_confidence"):
         assert np.array_equal(s_end[key], st_want[key]), key
+
+
+@pytest.mark.parametrize("name", ["small-rtty", "70-callerid-mdmf", "71-callerid-sdmf", "small-same", "small-1200",
+                                  "opt-sync-byte-600"])
+def test_live_receiver_prints_the_reference_output_however_the_stream_is_cut(name):
+    """minimodem_b200.LiveReceiver (stream_push -> rx_batch -> decode_batch, all on the device): the
+    audio of a reference vector fed in random chunks -- a different cut for every stream -- must add
+    up to what the unmodified reference CLI printed for the whole file."""
+    case = refcases.BY_NAME[name]
+    g = gu.load(name)
+    _, rx = gu.modes(case)
+    a = gu.audio(case, g)
+    rng = np.random.default_rng(77)
+    nstreams, max_chunk = 4, 2048
+    names = dict(mark="f_mark", space="f_space", bandwidth="band_width", startbits="nstartbits", stopbits="nstopbits")
+    ov = {names.get(k, k): v for k, v in case["rx_mkw"].items() if k != "sample_rate"}
+    lr = mm.LiveReceiver(case["rx_mode"], sample_rate=rx.sample_rate, nstreams=nstreams, max_chunk=max_chunk,
+                         device=dev(), **ov)
+    fed = [0] * nstreams
+    text = [bytearray() for _ in range(nstreams)]
+
+    def take(out, cnt):
+        o, c = out.cpu().numpy(), cnt.cpu().numpy()
+        for i in range(nstreams):
+            text[i] += bytes(o[i, :c[i]])
+
+    while any(f < a.size for f in fed):
+        chunk = np.zeros((nstreams, max_chunk), np.float32)
+        clen = np.zeros(nstreams, np.int32)
+        for i in range(nstreams):
+            k = int(min(rng.integers(1, max_chunk + 1) if i else max_chunk, a.size - fed[i]))
+            if i == 1:
+                k = min(k, 333)                                # one stream trickles in
+            chunk[i, :k] = a[fed[i]:fed[i] + k]
+            clen[i] = k
+            fed[i] += k
+        take(*lr.feed(torch.from_numpy(chunk).to(dev()), torch.from_numpy(clen).to(dev())))
+    take(*lr.finish())
+    torch.cuda.synchronize()
+    assert int(lr.dropped.sum()) == 0
+    for i in range(nstreams):
+        assert bytes(text[i]) == bytes(g["stdout"]), i
