@@ -1074,7 +1074,12 @@ extern "C" void *fsk_b200_cuda_engine_new(void)
     if ((e = getenv("FSK_B200_SPLIT"))) ce->split = atoi(e);
     ce->fill = 0;		/* see the dispatch in fsk_b200_cuda_rx_batch */
     if ((e = getenv("FSK_B200_FILL"))) ce->fill = atoi(e);
-    ce->slab_bytes = (size_t)256 << 20;
+    /* 1 GiB of float samples per slab, two slabs in flight.  A slab is one rx launch, and a launch of a
+     * few hundred streams is latency-bound (it cannot fill the SMs: ~3 ms however few streams), so the
+     * copy of the next slab has to last longer than that to hide it: at 54 GB/s a 256 MiB slab of
+     * int16 samples (128 MiB on the wire) copies in 2.5 ms -- measured 21 instead of 27 Gsamples/s --
+     * while 1 GiB slabs leave a wide margin for both sample formats. */
+    ce->slab_bytes = (size_t)1 << 30;
     if ((e = getenv("FSK_B200_SLAB_BYTES")) && atoll(e) > 0) ce->slab_bytes = (size_t)atoll(e);
     return ce;
 }
@@ -1459,7 +1464,7 @@ static int rx_batch_host_common(CudaEngine *ce, const fsk_b200_geom *g, const fs
 	const void *host_samples, int elem, size_t nstreams, size_t stride, uint32_t nsamples_all,
 	fsk_b200_frame *host_frames, uint32_t max_frames, fsk_b200_stream_state *host_states)
 {
-    /* slab = as many streams as fit ~256 MiB of float samples (two slabs in flight) */
+    /* slab = as many streams as fit slab_bytes of float samples (two slabs in flight) */
     size_t slab = ce->slab_bytes / (stride * sizeof(float));
     if (slab < 1) slab = 1;
     if (slab > nstreams) slab = nstreams;
