@@ -1074,11 +1074,11 @@ extern "C" void *fsk_b200_cuda_engine_new(void)
     if ((e = getenv("FSK_B200_SPLIT"))) ce->split = atoi(e);
     ce->fill = 0;		/* see the dispatch in fsk_b200_cuda_rx_batch */
     if ((e = getenv("FSK_B200_FILL"))) ce->fill = atoi(e);
-    /* 1 GiB of float samples per slab, two slabs in flight.  A slab is one rx launch, and a launch of a
-     * few hundred streams is latency-bound (it cannot fill the SMs: ~3 ms however few streams), so the
-     * copy of the next slab has to last longer than that to hide it: at 54 GB/s a 256 MiB slab of
-     * int16 samples (128 MiB on the wire) copies in 2.5 ms -- measured 21 instead of 27 Gsamples/s --
-     * while 1 GiB slabs leave a wide margin for both sample formats. */
+    /* 1 GiB of float samples per slab, two slabs in flight.  With 256 MiB slabs the float path ran at
+     * the PCIe rate (54 GB/s) but the int16 path at 78 % of it: about 0.7 ms per slab were not hidden
+     * behind the next copy (a slab is one conversion + one rx launch of only ~350 streams; which part
+     * of that stayed exposed was not isolated).  Fewer, larger slabs amortise whatever it is; the
+     * round-1 numbers were taken with 256 MiB. */
     ce->slab_bytes = (size_t)1 << 30;
     if ((e = getenv("FSK_B200_SLAB_BYTES")) && atoll(e) > 0) ce->slab_bytes = (size_t)atoll(e);
     return ce;
