@@ -1074,12 +1074,12 @@ extern "C" void *fsk_b200_cuda_engine_new(void)
     if ((e = getenv("FSK_B200_SPLIT"))) ce->split = atoi(e);
     ce->fill = 0;		/* see the dispatch in fsk_b200_cuda_rx_batch */
     if ((e = getenv("FSK_B200_FILL"))) ce->fill = atoi(e);
-    /* 1 GiB of float samples per slab, two slabs in flight.  With 256 MiB slabs the float path ran at
-     * the PCIe rate (54 GB/s) but the int16 path at 78 % of it: about 0.7 ms per slab were not hidden
-     * behind the next copy (a slab is one conversion + one rx launch of only ~350 streams; which part
-     * of that stayed exposed was not isolated).  Fewer, larger slabs amortise whatever it is; the
-     * round-1 numbers were taken with 256 MiB. */
-    ce->slab_bytes = (size_t)1 << 30;
+    /* 256 MiB of samples ON THE WIRE per slab, two slabs in flight: the float path runs at the PCIe
+     * rate with that (54 GB/s).  The int16 path, measured with slabs of the same stream count (128 MiB
+     * on the wire), reached 78 % of it -- about 0.7 ms per slab stayed exposed (one conversion plus
+     * one rx launch of ~350 streams; which part was not isolated) -- so its slabs now carry the same
+     * number of bytes, i.e. twice the streams. */
+    ce->slab_bytes = (size_t)256 << 20;
     if ((e = getenv("FSK_B200_SLAB_BYTES")) && atoll(e) > 0) ce->slab_bytes = (size_t)atoll(e);
     return ce;
 }
@@ -1464,8 +1464,8 @@ static int rx_batch_host_common(CudaEngine *ce, const fsk_b200_geom *g, const fs
 	const void *host_samples, int elem, size_t nstreams, size_t stride, uint32_t nsamples_all,
 	fsk_b200_frame *host_frames, uint32_t max_frames, fsk_b200_stream_state *host_states)
 {
-    /* slab = as many streams as fit slab_bytes of float samples (two slabs in flight) */
-    size_t slab = ce->slab_bytes / (stride * sizeof(float));
+    /* slab = as many streams as make slab_bytes on the wire (two slabs in flight) */
+    size_t slab = ce->slab_bytes / (stride * (size_t)elem);
     if (slab < 1) slab = 1;
     if (slab > nstreams) slab = nstreams;
     if (ce->slab_streams < slab || ce->slab_stride != stride || ce->slab_max_frames < max_frames) {

@@ -764,9 +764,10 @@ def test_uic_frames_end_to_end():
 
 @pytest.mark.parametrize("fmt", ["f32", "s16"])
 def test_host_buffer_path_in_many_slabs(fmt, monkeypatch):
-    """fsk_b200_rx_batch_host splits a batch into slabs (1 GiB of samples by default) and keeps two in flight; with the
-    slab shrunk to two streams, 7 streams take 4 slabs (the last one partial) on alternating
-    buffers -- records and states must equal the one-launch device path, stream by stream."""
+    """fsk_b200_rx_batch_host splits a batch into slabs (256 MiB on the wire by default) and keeps two in
+    flight; with the slab shrunk to two float streams (four int16 ones), 7 streams take 4 (2) slabs, the
+    last one partial, on alternating buffers -- records and states must equal the one-launch device
+    path, stream by stream."""
     case = refcases.BY_NAME["small-1200"]
     g = gu.load(case["name"])
     a = gu.audio(case, g)
