@@ -1,0 +1,45 @@
+"""bench.py's output contract, as far as it can be checked without a GPU: the reference arm
+(`--impl reference`, the unmodified src/fsk.c on the host cores) prints ONE JSON line with the keys
+the driver reads; under a multi-rank launch only rank 0 prints."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+import orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def run_bench(extra_env=None):
+    env = dict(os.environ, **(extra_env or {}))
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "0", "--cpu-streams", "8", "--nsamples", "48000"],
+                       cwd=ROOT, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=900)
+    assert r.returncode == 0, r.stderr[-800:]
+    return [ln for ln in r.stdout.decode().splitlines() if ln.strip()]
+
+
+def test_reference_arm_prints_one_contract_line():
+    lines = run_bench()
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference"
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e", "gpu_launches"):
+        assert key in d, key
+    assert d["metric"].startswith("audio Msamples/s demodulated") and d["unit"] == "Msamples/s"
+    assert d["higher_is_better"] is True and d["vs_baseline"] is None and d["gpu_launches"] == 0
+    assert "workload" in d["config"] and "model" not in d["config"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == ("reference" if orc.have_ref() else "port") and cb["cores"] >= 1 and cb["value"] > 0
+    assert cb["value"] == d["value"] == d["e2e"]["value"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    if orc.have_ref():
+        assert "not FFTW" in cb["sample"]           # the stand-in FFT is named, whichever it is
+
+
+def test_reference_arm_other_ranks_stay_silent():
+    assert run_bench({"RANK": "1", "LOCAL_RANK": "1", "WORLD_SIZE": "2"}) == []
