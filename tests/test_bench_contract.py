@@ -43,3 +43,19 @@ def test_reference_arm_prints_one_contract_line():
 
 def test_reference_arm_other_ranks_stay_silent():
     assert run_bench({"RANK": "1", "LOCAL_RANK": "1", "WORLD_SIZE": "2"}) == []
+
+
+def test_recorded_gpu_line_has_the_contract_keys():
+    """profiles/r1_bench_n1.json: the line `python bench.py` printed on a B200 at the end of round 1."""
+    d = json.loads(open(os.path.join(ROOT, "profiles", "r1_bench_n1.json")).read().strip().splitlines()[-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+        assert key in d, key
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert r["traffic"] and 0.99 < r["traffic"] / r["algorithmic_bytes"] < 1.01      # every sample read once
+    assert d["n_gpus"] == 1 and d["steps"] >= 1 and d["warmup"] >= 3 and d["gpu_launches"] >= d["steps"]
+    assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
+    assert d["e2e"]["value"] < d["value"]                       # host buffers: PCIe-bound, not a copy of `value`
+    assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    assert "workload" in d["config"] and d["dtype"] == "f32" and d["data"] == "synthetic"
