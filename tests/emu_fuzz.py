@@ -139,3 +139,25 @@ def test_dropouts_bursts_and_resume(mi, seed):
         raise AssertionError("streams did not finish")
     for i in range(len(streams)):
         T.compare_frames(T.as_oracle_frames(got[i]), wants[i]["frames"], "%s stream %d resumed" % (mode, i))
+
+
+import refcases  # noqa: E402
+
+
+@pytest.mark.parametrize("case", refcases.MORE, ids=[c["name"] for c in refcases.MORE])
+def test_second_batch_of_option_vectors(case):
+    """tests/refcases.py MORE: runs of the unmodified reference CLI that are on the CPU lists only;
+    here the emulated kernels have to reproduce their records, decoded bytes and stat lines."""
+    if case["ring_limited"]:
+        # the kernels follow the flat semantic: all of the text, of which the reference printed the start
+        g = T.gu.load(case["name"])
+        _, rx = T.gu.modes(case)
+        a = T.gu.audio(case, g)
+        eng, _ = T.engine_for(case)
+        (recs,), st = T.rx_on_gpu(eng, [a])
+        got = T.as_oracle_frames(recs)
+        T.compare_frames(got, orc.rx_run(rx, a, literal=False)["frames"], case["name"])
+        out = orc.decode_records(rx, refcases.decoder_of(case, rx), orc.frame_records(got))
+        assert out == bytes(g["text"]) and out.startswith(bytes(g["stdout"]))
+        return
+    T.test_rx_batch_on_reference_vectors(case)

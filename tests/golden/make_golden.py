@@ -126,7 +126,7 @@ def main():
     assert orc.build_ref(), "needs /root/reference"
     only = set(sys.argv[1:])
     with tempfile.TemporaryDirectory() as tmp:
-        for case in refcases.EVERY + refcases.CLI_ONLY:
+        for case in refcases.EVERY + refcases.CLI_ONLY + refcases.MORE:
             if only and case["name"] not in only:
                 continue
             out, r = run_case(case, tmp)

@@ -14,8 +14,11 @@ FLT_EPSILON = float(np.finfo(np.float32).eps)
 
 def _case(name, text, tx, rx=None, mode="1200", mkw=None, rx_mode=None, rx_mkw=None,
           amplitude=1.0, lut=4096, float_samples=False, rxnoise=0.0, rx_one=False,
-          perfect=False, tx_ascii=False, bins=False, audio=False):
-    return dict(name=name, text=text, tx=tx, rx=rx if rx is not None else tx, mode=mode,
+          perfect=False, tx_ascii=False, bins=False, audio=False, ring_limited=False):
+    """ring_limited: the reference stops early on this input because of how it sizes and refills its
+    sample ring; only the oracle's LITERAL mode reproduces that, the batched
+    (flat) semantic decodes the whole stream and the reference's output is a prefix of it."""
+    return dict(ring_limited=ring_limited, name=name, text=text, tx=tx, rx=rx if rx is not None else tx, mode=mode,
                 mkw=mkw or {}, rx_mode=rx_mode or mode, rx_mkw=rx_mkw if rx_mkw is not None else (mkw or {}),
                 amplitude=amplitude, lut=lut, float_samples=float_samples, rxnoise=rxnoise,
                 rx_one=rx_one, perfect=perfect, tx_ascii=tx_ascii, bins=bins, audio=audio)
@@ -133,6 +136,30 @@ def decoder_of(case, rx_mode):
     return "binary" if "--binary-output" in case["rx"] else rx_mode.decoder
 
 
+# A second batch of option runs: they pin the oracle on the CPU and the emulated kernels
+# (tests/emu_fuzz.py); not on the B200 list (that one is long enough).
+MORE = [
+    _case("more-v21", _OPT_TEXT, ["V.21"], mode="V.21", audio=True),
+    _case("more-6bit-3start", _OPT_TEXT, ["1200", "--startbits", "3", "--stopbits", "1.0"],
+          mkw=dict(n_data_bits=8, startbits=3, stopbits=1.0), audio=True),
+    _case("more-12000-96000", _OPT_TEXT, ["12000", "--samplerate", "96000"], mode="12000",
+          mkw=dict(sample_rate=96000), audio=True),
+    _case("more-1200-11025", _OPT_TEXT, ["1200", "--samplerate", "11025"], mkw=dict(sample_rate=11025), audio=True),
+    _case("more-1200-bw100", _OPT_TEXT, ["1200", "-b", "100"], mkw=dict(bandwidth=100.0), audio=True),
+    _case("more-tdd-inverted", b"TDD INVERTED 123\n", ["tdd", "--inverted"], mode="tdd", mkw=dict(inverted=True),
+          audio=True),
+    _case("more-same-msb", b"ZCZC-MSB-FIRST\n", ["same", "--msb-first"], mode="same", mkw=dict(msb_first=True),
+          audio=True),
+    # 8 data + 1 start + 3 stop bits: the advance after a frame exceeds the half-filled sample ring and
+    # the reference's loop ends after the first frame (src/minimodem.c:1150-1152)
+    _case("more-150-stop3", _OPT_TEXT, ["150", "--stopbits", "3.0", "--samplerate", "16000"], mode="150",
+          mkw=dict(sample_rate=16000, stopbits=3.0), audio=True, ring_limited=True),
+    _case("more-volume-E", _OPT_TEXT, ["1200", "--volume", "E"], amplitude=FLT_EPSILON, audio=True),
+    _case("more-quiet-noise", _OPT_TEXT, ["1200", "--float-samples", "--volume", "0.05"],
+          rx=["1200", "--Xrxnoise", "0.02"], amplitude=0.05, float_samples=True, rxnoise=float(np.float32(0.02)),
+          audio=True),
+]
+
 EVERY = ALL + OPTIONS
 
 # Runs that only the whole CLI can make (the oracle's rx loop has no --auto-carrier): they pin the
@@ -145,4 +172,4 @@ CLI_ONLY = [
           rx=["rtty", "--samplerate", "8000", "--auto-carrier"], mode="rtty", mkw=dict(sample_rate=8000), audio=True),
 ]
 
-BY_NAME = {c["name"]: c for c in EVERY + CLI_ONLY}
+BY_NAME = {c["name"]: c for c in EVERY + CLI_ONLY + MORE}

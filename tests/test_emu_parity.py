@@ -39,11 +39,12 @@ def test_reference_vectors_on_the_emulated_kernels_eager_copies():
 
 
 def test_random_modes_and_dropouts_on_the_emulated_kernels():
-    """tests/emu_fuzz.py: 64 random framings / rates / bit orders, and 24 streams that keep losing
-    and finding the carrier (also decoded in 3-frame record buffers with resume): oracle TX ->
-    emulated kernels -> records equal to the oracle's rx loop."""
-    tail = run_emulated("random_mode or dropouts", "late", 1200, module="emu_fuzz.py")
-    assert "88 passed" in tail
+    """tests/emu_fuzz.py: 64 random framings / rates / bit orders, 24 streams that keep losing and
+    finding the carrier (also decoded in 3-frame record buffers with resume): oracle TX -> emulated
+    kernels -> records equal to the oracle's rx loop; and the second batch of reference-CLI option
+    vectors (tests/refcases.py MORE)."""
+    tail = run_emulated("random_mode or dropouts or second_batch", "late", 1200, module="emu_fuzz.py")
+    assert "98 passed" in tail
 
 
 def test_the_emulator_itself():

@@ -9,7 +9,7 @@ import golden_util as gu
 import orc
 import refcases
 
-CASES = refcases.EVERY
+CASES = refcases.EVERY + refcases.MORE
 IDS = [c["name"] for c in CASES]
 
 
@@ -52,6 +52,11 @@ def test_rx_restatement_decodes_and_reports_like_reference(case):
     for literal in (True, False):
         r = orc.rx_run(rx, a, literal=literal, rxnoise=case["rxnoise"], rx_one=case["rx_one"])
         out = orc.ref_decode(rx, r["frames"], decoder=refcases.decoder_of(case, rx))
+        if case["ring_limited"] and not literal:
+            # the reference gave up early (its ring); the flat semantic goes on: same beginning, more text
+            assert out.startswith(bytes(g["stdout"])) and len(out) > len(bytes(g["stdout"]))
+            assert out == bytes(g["text"])
+            continue
         assert out == bytes(g["stdout"]), ("literal" if literal else "flat")
         want = gu.stat_lines(g)
         got = [orc.report_line(rx, rp) for rp in r["reports"]]
