@@ -199,7 +199,7 @@ def test_output_cap_counts_are_clamped_by_the_caller():
 GOLD = [c for c in refcases.ALL if c["name"] in (
     "01-self-test-1200", "03-self-test-rtty", "60-multibyte", "70-callerid-mdmf", "71-callerid-sdmf",
     "80-SAME", "81-ascii7", "81-tdd", "21-rate-slop-308", "40-noise-0.50", "small-rtty", "small-same")]
-GOLD += refcases.OPTIONS
+GOLD += refcases.OPTIONS + [c for c in refcases.MORE if not c["ring_limited"]]
 
 
 @pytest.mark.parametrize("case", GOLD, ids=[c["name"] for c in GOLD])

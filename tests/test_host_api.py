@@ -44,7 +44,7 @@ MODES = [("1200", {}), ("300", {}), ("rtty", {}), ("tdd", {}), ("same", {}), ("c
 
 
 # the option combinations minted from the reference CLI (tests/refcases.py OPTIONS), rx side
-MODES += [(c["rx_mode"], c["rx_mkw"]) for c in refcases.OPTIONS]
+MODES += [(c["rx_mode"], c["rx_mkw"]) for c in refcases.OPTIONS + refcases.MORE]
 
 
 def overrides_for(kw):
