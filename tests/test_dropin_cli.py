@@ -55,3 +55,37 @@ def test_reference_self_tests_pass_with_this_library_behind_the_reference_cli(tm
     # build they fail here in exactly the same way
     allowed = set() if have_bc else {"30-amplitude.test", "31-amplitude-float.test"}
     assert {t for t, _ in failed} <= allowed, failed
+
+
+@pytest.mark.ref
+@pytest.mark.parametrize("seed", range(40))
+def test_dropin_cli_equals_reference_cli_on_a_random_invocation(seed, tmp_path):
+    """The reference's main() on this library (emulated kernels) against the reference's main() on its
+    own src/fsk.c, for a random baud rate / sample rate / framing / bit order / tone pair: the same
+    stdout, the same CARRIER / NOCARRIER lines (confidence to the parity tolerance)."""
+    import numpy as np
+    import golden_util as gu
+    from test_oracle_fuzz_vs_cli import random_invocation
+    if not os.path.exists(DROPIN):
+        pytest.skip("oracle/_ref/minimodem_dropin not built")
+    rng = np.random.default_rng(9000 + seed)
+    mode, kw, tx_args, rx_args, flt, vol = random_invocation(rng)
+    text = bytes(rng.integers(32, 127, int(rng.integers(4, 30)), dtype=np.uint8)) + b"\n"
+    wav = str(tmp_path / "x.wav")
+    subprocess.run([orc.REF_CLI, "--tx", "--file", wav] + tx_args, input=text, check=True)
+    ref = subprocess.run([orc.REF_CLI, "--rx", "--file", wav] + rx_args, stdout=subprocess.PIPE,
+                         stderr=subprocess.PIPE, check=True)
+    env = dict(os.environ, LD_LIBRARY_PATH=emulation_as_product())
+    our = subprocess.run([DROPIN, "--rx", "--file", wav] + rx_args, env=env, stdout=subprocess.PIPE,
+                         stderr=subprocess.PIPE, timeout=600)
+    assert our.returncode == 0, our.stderr[-400:]
+    assert our.stdout == ref.stdout, (rx_args, our.stdout[:40], ref.stdout[:40])
+    a = [ln.split() for ln in our.stderr.decode().splitlines() if ln.startswith("###")]
+    b = [ln.split() for ln in ref.stderr.decode().splitlines() if ln.startswith("###")]
+    assert len(a) == len(b), (our.stderr, ref.stderr)
+    for fa, fb in zip(a, b):
+        if fa[1] == "NOCARRIER":
+            assert fa[:3] == fb[:3] and fa[4:] == fb[4:], (fa, fb)
+            assert gu.close(float(fa[3].split("=")[1]), float(fb[3].split("=")[1]), 2e-3, cond=gu.CONF_COND)
+        else:
+            assert fa == fb
