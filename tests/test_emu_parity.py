@@ -43,8 +43,9 @@ def test_random_modes_and_dropouts_on_the_emulated_kernels():
     finding the carrier (also decoded in 3-frame record buffers with resume): oracle TX -> emulated
     kernels -> records equal to the oracle's rx loop; and the second batch of reference-CLI option
     vectors (tests/refcases.py MORE)."""
-    tail = run_emulated("random_mode or dropouts or second_batch", "late", 1200, module="emu_fuzz.py")
-    assert "98 passed" in tail
+    tail = run_emulated("random_mode or dropouts or second_batch or batched_kernels_print", "late", 1200,
+                        module="emu_fuzz.py")
+    assert "failed" not in tail and ("137 passed" in tail or "138 passed" in tail)     # one seed is ring-limited
 
 
 def test_the_emulator_itself():
