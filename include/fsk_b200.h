@@ -188,7 +188,12 @@ typedef struct fsk_b200_stream_state {
     float	confidence_total;
     float	amplitude_total;
     uint32_t	nframes_decoded;
-    uint32_t	reserved[3];
+    /* statistics, accumulated over launches (not part of the reference's state): frame candidates
+     * analysed (fsk_frame_analyze calls, src/fsk.c:487) and searches run (fsk_find_frame calls,
+     * src/minimodem.c:1265/:1373) by the fast rx kernel; 0 on the generic path */
+    uint32_t	stat_candidates;
+    uint32_t	stat_searches;
+    uint32_t	reserved;
 } fsk_b200_stream_state;
 
 typedef struct fsk_b200_engine fsk_b200_engine;

@@ -64,7 +64,7 @@ class StreamState(C.Structure):
                 ("peak_confidence", C.c_float), ("done", C.c_uint32),
                 ("carrier_nsamples", C.c_uint64), ("confidence_total", C.c_float),
                 ("amplitude_total", C.c_float), ("nframes_decoded", C.c_uint32),
-                ("reserved", C.c_uint32 * 3)]
+                ("stat_candidates", C.c_uint32), ("stat_searches", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 STATE_DTYPE = np.dtype([("pos", "<u8"), ("nframes", "<u4"), ("carrier", "<u4"),
@@ -72,7 +72,7 @@ STATE_DTYPE = np.dtype([("pos", "<u8"), ("nframes", "<u4"), ("carrier", "<u4"),
                         ("peak_confidence", "<f4"), ("done", "<u4"),
                         ("carrier_nsamples", "<u8"), ("confidence_total", "<f4"),
                         ("amplitude_total", "<f4"), ("nframes_decoded", "<u4"),
-                        ("reserved", "<u4", (3,))])
+                        ("stat_candidates", "<u4"), ("stat_searches", "<u4"), ("reserved", "<u4")])
 STATE_WORDS = STATE_DTYPE.itemsize // 4
 
 

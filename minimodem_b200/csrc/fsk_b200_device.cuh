@@ -651,7 +651,7 @@ template <int G, int W, int L>
 __device__ __forceinline__ Found find_frame_fast_body(const Ring rg, unsigned pos_off,
 	const fsk_b200_geom &geo, const LaneWin<W> lw, int sel, unsigned tw_s,
 	unsigned g, unsigned gmask, unsigned try_first, unsigned try_max, unsigned try_step, float limit,
-	int ready = 0, bool pending = false)
+	int ready, bool pending, unsigned &ncand)
 {
     /* pending: the caller's latest copies into the ring are still in flight, and `ready` samples
      * from pos_off on are known to have landed; the first candidate waits as late as it can */
@@ -665,6 +665,7 @@ __device__ __forceinline__ Found find_frame_fast_body(const Ring rg, unsigned po
 	    continue;
 	unsigned lo, hi;
 	float a;
+	ncand++;
 	const float c = frame_analyze_fast<G, W, L>(rg, ring_wrap(pos_off + (unsigned)t, rg.R), geo, lw, sel,
 		tw_s, g, gmask, lo, hi, a, ready - t, pending);
 	if (best.confidence < c) {			/* NaN and negatives never win */
@@ -683,8 +684,9 @@ __device__ __noinline__ Found find_frame_fast(const Ring rg, unsigned pos_off,
 	unsigned g, unsigned gmask, unsigned try_first, unsigned try_max, unsigned try_step, float limit,
 	int ready = 0, bool pending = false)
 {
+    unsigned ncand = 0;
     return find_frame_fast_body<G, W, L>(rg, pos_off, geo, lw, sel, tw_s, g, gmask, try_first, try_max,
-	    try_step, limit, ready, pending);
+	    try_step, limit, ready, pending, ncand);
 }
 
 /* ------------------------------------------------------------------------ */

@@ -447,6 +447,14 @@ int fsk_b200_rx_batch(fsk_b200_engine *e, const float *samples, size_t nstreams,
 	fsk_b200_set_error("rx_batch: NULL argument");
 	return -EINVAL;
     }
+    if (!nsamples && (size_t)nsamples_all > stride) {
+	fsk_b200_set_error("rx_batch: nsamples_all (%u) exceeds the row stride (%zu)", nsamples_all, stride);
+	return -EINVAL;
+    }
+    if (nstreams > 0x7fffffffu) {
+	fsk_b200_set_error("rx_batch: at most 2^31-1 streams per call");
+	return -EINVAL;
+    }
     return fsk_b200_cuda_rx_batch(e->ce, &e->geom, &e->loopc, samples, nstreams, stride,
 	    nsamples, nsamples_all, frames, max_frames, states, stream);
 }
@@ -455,9 +463,17 @@ int fsk_b200_rx_batch(fsk_b200_engine *e, const float *samples, size_t nstreams,
 
 uint32_t fsk_b200_stream_window(const fsk_b200_rx_params *p)
 {
-    /* the farthest sample a search that starts at `pos` can touch: its last candidate plus the span
-     * of the frame's bit windows (src/fsk.c:481, :204) */
-    return p ? p->try_max_nocarrier - 1u + p->span_nsamples : 0u;
+    /* the farthest sample a loop iteration that starts at `pos` can depend on: its last candidate
+     * plus the span of the frame's bit windows (src/fsk.c:481, :204) -- or, for frames with more stop
+     * bits than the search string covers (frame_n_bits > expect_n_bits, e.g. 3 stop bits), the largest
+     * advance frame_start + frame_nsamples - overscan (src/minimodem.c:1407): an iteration held back
+     * by this many samples can neither read past the chunk nor hit the end-of-input exit of :1151
+     * after it has already recorded its frame */
+    if (!p)
+	return 0u;
+    const unsigned adv = p->frame_nsamples > p->nsamples_overscan ? p->frame_nsamples - p->nsamples_overscan : 0u;
+    const unsigned tmax = p->try_max_nocarrier > p->try_max_carrier ? p->try_max_nocarrier : p->try_max_carrier;
+    return tmax - 1u + (p->span_nsamples > adv ? p->span_nsamples : adv);
 }
 
 int fsk_b200_engine_set_holdback(fsk_b200_engine *e, uint32_t nsamples)
@@ -500,6 +516,11 @@ int fsk_b200_rx_batch_host(fsk_b200_engine *e, const float *host_samples, size_t
 	return 0;
     if (!host_samples || !host_frames || !host_states || (stride & 3) || max_frames == 0) {
 	fsk_b200_set_error("rx_batch_host: bad argument (stride must be a multiple of 4)");
+	return -EINVAL;
+    }
+    if ((size_t)nsamples_all > stride || nstreams > 0x7fffffffu) {
+	fsk_b200_set_error("rx_batch_host: nsamples_all (%u) exceeds the row stride (%zu), or too many streams",
+		nsamples_all, stride);
 	return -EINVAL;
     }
     return fsk_b200_cuda_rx_batch_host(e->ce, &e->geom, &e->loopc, host_samples, nstreams,

@@ -220,7 +220,8 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
 	if (st.done)
 	    continue;
 	const float *x = a.samples + (size_t)s * a.stride;
-	const unsigned n = a.nsamples ? a.nsamples[s] : a.nsamples_all;
+	/* a row never extends past its stride (per-stream lengths are caller data) */
+	const unsigned n = (unsigned)min((size_t)(a.nsamples ? a.nsamples[s] : a.nsamples_all), a.stride);
 	fsk_b200_frame *out = a.frames + (size_t)s * a.max_frames;
 
 	unsigned pos = (unsigned)st.pos;
@@ -231,6 +232,7 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
 	float confidence_total = st.confidence_total, amplitude_total = st.amplitude_total;
 	unsigned nframes_decoded = st.nframes_decoded;
 	unsigned done = 0;
+	unsigned ncand = 0, nsearch = 0;	/* statistics: candidates analysed, searches run */
 
 	/* ring bookkeeping (MODE 0): ring offset of `pos`, and the absolute index up to
 	 * which the ring content has been REQUESTED (copies issued or zeros stored) */
@@ -395,8 +397,9 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
 		float limit = lc.confidence_search_limit;
 		int which = sel;
 		for (int pass = 0;; pass++) {
+		    nsearch++;
 		    const Found f = find_frame_fast_body<G, W, L>(rg, pos_off, geo, lw, which, tw_s, g,
-			    gmask, try_first, try_max, step, limit, ready, pending);	/* :1265, :1378 */
+			    gmask, try_first, try_max, step, limit, ready, pending, ncand);	/* :1265, :1378 */
 		    if (pass) {
 			refined = f;
 			break;
@@ -545,6 +548,8 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
 	    st.amplitude_total = amplitude_total;
 	    st.nframes_decoded = nframes_decoded;
 	    st.done = done;
+	    st.stat_candidates += ncand;
+	    st.stat_searches += nsearch;
 	    a.states[s] = st;
 	}
 	__syncwarp(gmask);
@@ -1084,6 +1089,19 @@ extern "C" void *fsk_b200_cuda_engine_new(void)
     return ce;
 }
 
+/* an engine belongs to the device that was current when it was created: its buffers and the
+ * caller's device pointers must live there, and launches go to the CURRENT device */
+static int engine_device_check(const CudaEngine *ce, const char *what)
+{
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess || cur != ce->device) {
+	fsk_b200_set_error("%s: engine was created on CUDA device %d but device %d is current", what,
+		ce->device, cur);
+	return -EINVAL;
+    }
+    return 0;
+}
+
 extern "C" void fsk_b200_cuda_engine_destroy(void *p)
 {
     CudaEngine *ce = (CudaEngine *)p;
@@ -1162,8 +1180,11 @@ extern "C" int fsk_b200_cuda_set_table(void *p, int fftsize, unsigned b_mark, un
 	}
 	ce->tw_cap = bit_nsamples;
     }
-    /* synchronous copy on the legacy stream: ordered before any later launch */
+    /* synchronous copy from pageable memory, then a device-wide synchronise: the library's own
+     * streams and the caller's may be cudaStreamNonBlocking, which the legacy stream does not order */
     cudaError_t err = cudaMemcpy(ce->d_tw, h, sizeof(float4) * bit_nsamples, cudaMemcpyHostToDevice);
+    if (err == cudaSuccess)
+	err = cudaDeviceSynchronize();
     free(h);
     if (err != cudaSuccess) {
 	fsk_b200_set_error("set_table: %s", cudaGetErrorString(err));
@@ -1358,6 +1379,8 @@ extern "C" int fsk_b200_cuda_find_frame_batch(void *p, const fsk_b200_geom *g, c
 	fsk_b200_set_error("find_frame_batch: twiddle table not set");
 	return -EINVAL;
     }
+    if (engine_device_check(ce, "find_frame_batch"))
+	return -EINVAL;
     Shape sh;
     /* the ring is sized for the widest search of the rx loop: 1.5 bits + span */
     pick_shape(ce, g, g->span + 2u * g->bit_nsamples + 8u, 0, nstreams, &sh);
@@ -1418,6 +1441,8 @@ extern "C" int fsk_b200_cuda_rx_batch(void *p, const fsk_b200_geom *g, const fsk
 	fsk_b200_set_error("rx_batch: twiddle table not set");
 	return -EINVAL;
     }
+    if (engine_device_check(ce, "rx_batch"))
+	return -EINVAL;
     Shape sh;
     const unsigned tmax = lc->try_max_nocarrier > lc->try_max_carrier
 	? lc->try_max_nocarrier : lc->try_max_carrier;
@@ -1469,6 +1494,8 @@ static int rx_batch_host_common(CudaEngine *ce, const fsk_b200_geom *g, const fs
     if (slab < 1) slab = 1;
     if (slab > nstreams) slab = nstreams;
     if (ce->slab_streams < slab || ce->slab_stride != stride || ce->slab_max_frames < max_frames) {
+	/* forget the old shape first: a failed allocation below must not leave it looking valid */
+	ce->slab_streams = ce->slab_stride = ce->slab_max_frames = 0;
 	for (int i = 0; i < 2; i++) {
 	    cudaFree(ce->d_slab[i]); ce->d_slab[i] = NULL;
 	    cudaFree(ce->d_slab_frames[i]); ce->d_slab_frames[i] = NULL;

@@ -179,6 +179,17 @@ unsigned long long orc_rx_many(const orc_rx_config *cfg, const float *samples,
 		orc_plan_destroy_fn plan_destroy,
 		unsigned *frames_per_stream, unsigned long long *bits_xor_per_stream);
 
+/* Persistent worker pool for the CPU timing arms (bench.py): pinned workers created once, one
+ * plan per worker built once, contiguous stream blocks copied into pool memory by the worker
+ * that will demodulate them (first touch), pass time taken inside around the start/stop barriers. */
+typedef struct orc_pool orc_pool;
+orc_pool *orc_pool_new(const orc_rx_config *cfg, int nthreads, orc_plan_new_fn plan_new,
+		orc_find_frame_fn find_frame, orc_plan_destroy_fn plan_destroy);
+int orc_pool_load(orc_pool *p, const float *samples, size_t nstreams, size_t src_stride, size_t nsamples);
+double orc_pool_run(orc_pool *p, unsigned long long *total, unsigned *frames_per_stream,
+		unsigned long long *bits_xor_per_stream);
+void orc_pool_free(orc_pool *p);
+
 /* ---- tx: restates src/minimodem.c:81-250 + src/simple-tone-generator.c -- */
 typedef struct orc_tx_config {
     float sample_rate;		/* unsigned in the reference, :534 */

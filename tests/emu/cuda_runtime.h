@@ -328,6 +328,7 @@ static inline const char *cudaGetErrorString(cudaError_t e) { return e == cudaSu
 static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 static inline cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }
 static inline cudaError_t cudaGetDevice(int *d) { *d = 0; return cudaSuccess; }
+static inline cudaError_t cudaDeviceSynchronize(void) { return cudaSuccess; }
 static inline cudaError_t cudaDeviceGetAttribute(int *v, int attr, int)
 {
     /* the B200 figures the launch-shape logic is written for */

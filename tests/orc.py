@@ -149,6 +149,14 @@ def lib():
                                   C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.POINTER(C.c_uint), C.POINTER(C.c_ulonglong)]
         L.orc_rx_many.restype = C.c_ulonglong
+        L.orc_pool_new.argtypes = [C.POINTER(OrcRxConfig), C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_pool_new.restype = C.c_void_p
+        L.orc_pool_load.argtypes = [C.c_void_p, fp, C.c_size_t, C.c_size_t, C.c_size_t]
+        L.orc_pool_load.restype = C.c_int
+        L.orc_pool_run.argtypes = [C.c_void_p, C.POINTER(C.c_ulonglong), C.POINTER(C.c_uint),
+                                   C.POINTER(C.c_ulonglong)]
+        L.orc_pool_run.restype = C.c_double
+        L.orc_pool_free.argtypes = [C.c_void_p]
         L.orc_tx_nsamples.argtypes = [C.POINTER(OrcTxConfig), C.c_size_t]
         L.orc_tx_nsamples.restype = C.c_size_t
         L.orc_tx_words.argtypes = [C.POINTER(OrcTxConfig), C.POINTER(C.c_uint), C.c_size_t, fp, C.c_size_t]
@@ -609,3 +617,51 @@ def rx_many(mode, samples, nsamples=None, nthreads=1, kind="port"):
                               pn, ff, pd, fps.ctypes.data_as(C.POINTER(C.c_uint)),
                               bx.ctypes.data_as(C.POINTER(C.c_ulonglong)))
     return int(total), fps, bx
+
+
+class RxPool:
+    """Persistent CPU worker pool for the timing arms (oracle/fsk_oracle.c, orc_pool_*): `nthreads`
+    workers pinned one per allowed CPU, one plan per worker built once, each worker owns a contiguous
+    block of streams that it copied into pool memory itself (first touch).  kind as in rx_many."""
+
+    def __init__(self, mode, nthreads=1, kind="port"):
+        self.cfg = mode.rx_config()
+        pn = ff = pd = None
+        if kind in ("reference", "reference-dfti"):
+            R = ref() if kind == "reference" else ref_dfti()
+            pn = C.cast(R.fsk_plan_new, C.c_void_p)
+            ff = C.cast(R.fsk_find_frame, C.c_void_p)
+            pd = C.cast(R.fsk_plan_destroy, C.c_void_p)
+        self._keep = (pn, ff, pd)
+        self.nthreads = int(nthreads)
+        self.h = lib().orc_pool_new(C.byref(self.cfg), self.nthreads, pn, ff, pd)
+        assert self.h
+        self.nstreams = 0
+
+    def load(self, samples, nsamples=None):
+        samples = np.ascontiguousarray(samples, np.float32)
+        self.nstreams, stride = samples.shape
+        self.nsamples = int(nsamples if nsamples is not None else stride)
+        rc = lib().orc_pool_load(self.h, fptr(samples.reshape(-1)), self.nstreams, stride, self.nsamples)
+        assert rc == 0
+
+    def run(self):
+        """One pass over the loaded streams: (seconds, total_frames, frames_per_stream, bits_xor)."""
+        fps = np.zeros(self.nstreams, np.uint32)
+        bx = np.zeros(self.nstreams, np.uint64)
+        total = C.c_ulonglong(0)
+        dt = lib().orc_pool_run(self.h, C.byref(total), fps.ctypes.data_as(C.POINTER(C.c_uint)),
+                                bx.ctypes.data_as(C.POINTER(C.c_ulonglong)))
+        assert dt >= 0.0, "a worker could not build its plan"
+        return float(dt), int(total.value), fps, bx
+
+    def close(self):
+        if self.h:
+            lib().orc_pool_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
