@@ -391,62 +391,19 @@ struct Found {
     unsigned start, bits_lo, bits_hi;
 };
 
-/* One candidate frame start, fast path.  Lane g of the group owns the windows
- * w = j*(G/L) + g/L (j < W) and, of each, the samples n = g%L, g%L + L, ...
- * Everything stays in registers: the per-bit (sig, noise, bit) values never go
- * to memory, and the frame statistics of src/fsk.c:271-336 are formed by
- * butterfly reductions over the group instead of a serial loop over the bits
- * (same terms, different but fixed summation order). */
-template <int G, int W, int L, bool WS = false>
-__device__ __forceinline__ float frame_analyze_fast(const Ring rg, unsigned cand_off,
-	const fsk_b200_geom &geo, const LaneWin<W> &lw, int sel, unsigned tw_s,
-	unsigned g, unsigned gmask_in, unsigned &bits_lo_out, unsigned &bits_hi_out, float &ampl_out,
-	int avail, bool &pending)
+/* From the (per-lane partial) sums of this lane's W windows to the frame statistic: the exchange
+ * between the L lanes of a window, the per-window decision (src/fsk.c:158-169, :211), the sums
+ * and the confidence (:271-336).  CONSEC: window j of the lane is bit wslot*W + j (MULTI) instead
+ * of j*(G/L) + wslot.  p[j] = first sample of window j (for the fp64 re-sum). */
+template <int G, int W, int L, bool WS, bool CONSEC>
+__device__ __forceinline__ float frame_finish(float (&acc)[W][4], const float *const (&p)[W],
+	const unsigned own_mask, const unsigned exp_bits, const fsk_b200_geom &geo, const float4 *tw, int sel,
+	unsigned g, unsigned gmask_in, unsigned &bits_lo_out, unsigned &bits_hi_out, float &ampl_out)
 {
-    /* WS ("warp-synchronous"): the caller guarantees that all 32 lanes are here together, so
-     * shuffles and votes use the constant full mask (the shuffle distances stay inside a
-     * group); with a run-time group mask the compiler has to guard every shuffle with a
-     * MATCH/VOTE sequence.  A rejected candidate is then zeroed at the end instead of
-     * returning early. */
     const unsigned gmask = WS ? 0xffffffffu : gmask_in;
-    /* ring and twiddles are handed over as shared-window addresses and turned back into
-     * pointers here, so that the compiler keeps them in the shared address space (LDS with
-     * 32-bit addresses and immediate offsets) even though this code is not inlined */
-    const float *ring = static_cast<const float *>(__cvta_shared_to_generic(rg.ring_s));
-    const float4 *tw = static_cast<const float4 *>(__cvta_shared_to_generic(tw_s));
-    /* cand_off: ring offset (< R) of the candidate's first sample */
-    constexpr unsigned WPP = G / L;		/* windows per pass */
-    const unsigned N = geo.bit_nsamples, nb = geo.n_bits, R = rg.R;
+    constexpr unsigned WPP = G / L;
+    const unsigned N = geo.bit_nsamples, nb = geo.n_bits;
     const unsigned part = g % L, wslot = g / L;
-
-    /* slots past n_bits read window 0: harmless, their results are dropped */
-    const float *p[W];
-#pragma unroll
-    for (int j = 0; j < W; j++)
-	p[j] = ring + ring_wrap(cand_off + lw.beg[j], R);
-
-    float acc[W][4];
-#pragma unroll
-    for (int j = 0; j < W; j++)
-	acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
-
-    /* `pending`: copies into this ring may still be in flight; `avail` samples from the
-     * candidate's first one are known to have landed */
-    constexpr int SJ = (FSK_STAGE_J < W) ? FSK_STAGE_J : 0;
-    if (SJ > 0) {
-	if (pending && (int)lw.a_end > avail) {
-	    cp_async_wait<0>();
-	    __syncwarp(gmask);
-	    pending = false;
-	}
-	corr_pass<0, SJ, W, L>(acc, p, tw, part, N);
-    }
-    if (pending) {
-	cp_async_wait<0>();
-	__syncwarp(gmask);
-	pending = false;
-    }
-    corr_pass<SJ, W, W, L>(acc, p, tw, part, N);
     constexpr int KW = (W + L - 1) / L;
 #ifdef FSK_NO_XCHG
     constexpr bool XCHG = false;
@@ -512,7 +469,7 @@ __device__ __forceinline__ float frame_analyze_fast(const Ring rg, unsigned cand
 	if (XCHG) {
 	    a0 = ax[k][0]; a1 = ax[k][1]; a2 = ax[k][2]; a3 = ax[k][3];
 	}
-	own[k] = (lw.own >> jsel) & 1u;
+	own[k] = (own_mask >> jsel) & 1u;
 	sig[k] = 0.f;
 	one[k] = false;
 	if (own[k]) {
@@ -534,11 +491,11 @@ __device__ __forceinline__ float frame_analyze_fast(const Ring rg, unsigned cand
 		mag_mark = sqrtf(frm * frm + fim * fim);
 		mag_space = sqrtf(frs * frs + fis * fis);
 	    }
-	    const unsigned w = jsel * WPP + wslot;
+	    const unsigned w = CONSEC ? wslot * (unsigned)W + jsel : jsel * WPP + wslot;
 	    one[k] = mag_mark > mag_space;			/* strict: tie -> space */
 	    sig[k] = one[k] ? mag_mark : mag_space;
 	    const float noise = one[k] ? mag_space : mag_mark;
-	    const unsigned e = (lw.exp >> (2u * (jsel + (sel ? (unsigned)W : 0u)))) & 3u;
+	    const unsigned e = (exp_bits >> (2u * (jsel + (sel ? (unsigned)W : 0u)))) & 3u;
 	    mismatch |= e != 2u && e != (one[k] ? 1u : 0u);	/* pass 1, :211 */
 	    if (noise > eps_u)					/* :279 */
 		tn += noise;
@@ -616,6 +573,66 @@ __device__ __forceinline__ float frame_analyze_fast(const Ring rg, unsigned cand
     return snr * (1.0f - divergence);				/* :336 */
 }
 
+/* One candidate frame start, fast path.  Lane g of the group owns the windows
+ * w = j*(G/L) + g/L (j < W) and, of each, the samples n = g%L, g%L + L, ...
+ * Everything stays in registers: the per-bit (sig, noise, bit) values never go
+ * to memory, and the frame statistics of src/fsk.c:271-336 are formed by
+ * butterfly reductions over the group instead of a serial loop over the bits
+ * (same terms, different but fixed summation order). */
+template <int G, int W, int L, bool WS = false>
+__device__ __forceinline__ float frame_analyze_fast(const Ring rg, unsigned cand_off,
+	const fsk_b200_geom &geo, const LaneWin<W> &lw, int sel, unsigned tw_s,
+	unsigned g, unsigned gmask_in, unsigned &bits_lo_out, unsigned &bits_hi_out, float &ampl_out,
+	int avail, bool &pending)
+{
+    /* WS ("warp-synchronous"): the caller guarantees that all 32 lanes are here together, so
+     * shuffles and votes use the constant full mask (the shuffle distances stay inside a
+     * group); with a run-time group mask the compiler has to guard every shuffle with a
+     * MATCH/VOTE sequence.  A rejected candidate is then zeroed at the end instead of
+     * returning early. */
+    const unsigned gmask = WS ? 0xffffffffu : gmask_in;
+    /* ring and twiddles are handed over as shared-window addresses and turned back into
+     * pointers here, so that the compiler keeps them in the shared address space (LDS with
+     * 32-bit addresses and immediate offsets) even though this code is not inlined */
+    const float *ring = static_cast<const float *>(__cvta_shared_to_generic(rg.ring_s));
+    const float4 *tw = static_cast<const float4 *>(__cvta_shared_to_generic(tw_s));
+    /* cand_off: ring offset (< R) of the candidate's first sample */
+    constexpr unsigned WPP = G / L;		/* windows per pass */
+    const unsigned N = geo.bit_nsamples, nb = geo.n_bits, R = rg.R;
+    const unsigned part = g % L, wslot = g / L;
+
+    /* slots past n_bits read window 0: harmless, their results are dropped */
+    const float *p[W];
+#pragma unroll
+    for (int j = 0; j < W; j++)
+	p[j] = ring + ring_wrap(cand_off + lw.beg[j], R);
+
+    float acc[W][4];
+#pragma unroll
+    for (int j = 0; j < W; j++)
+	acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+
+    /* `pending`: copies into this ring may still be in flight; `avail` samples from the
+     * candidate's first one are known to have landed */
+    constexpr int SJ = (FSK_STAGE_J < W) ? FSK_STAGE_J : 0;
+    if (SJ > 0) {
+	if (pending && (int)lw.a_end > avail) {
+	    cp_async_wait<0>();
+	    __syncwarp(gmask);
+	    pending = false;
+	}
+	corr_pass<0, SJ, W, L>(acc, p, tw, part, N);
+    }
+    if (pending) {
+	cp_async_wait<0>();
+	__syncwarp(gmask);
+	pending = false;
+    }
+    corr_pass<SJ, W, W, L>(acc, p, tw, part, N);
+    return frame_finish<G, W, L, WS, false>(acc, p, lw.own, lw.exp, geo, tw, sel, g, gmask_in, bits_lo_out,
+	    bits_hi_out, ampl_out);
+}
+
 /* The zig-zag search of src/fsk.c:477-502 run warp-synchronously: every lane of the warp
  * takes every trip of the loop; a group whose search is over (or that has no stream, `on`
  * false) rides along on candidate 0 and drops the result.  SIMT would spend those trips
@@ -689,6 +706,222 @@ __device__ __noinline__ Found find_frame_fast(const Ring rg, unsigned pos_off,
 	    try_step, limit, ready, pending, ncand);
 }
 
+/* ======================================================================== */
+/* MULTI: shared-segment search (plan: fsk_b200_internal.h, fsk_b200_mplan)  */
+/* ======================================================================== */
+/* The candidates of one search read the same samples cut at different places.  A batch of up to
+ * three candidates lays a grid of bit periods (length N = bit_nsamples, the windows tile) over the
+ * ring, anchored at one candidate, and cuts every period at the offsets rho1 <= rho2 where the
+ * other candidates' windows begin.  Lane (slot, part) owns the W CONSECUTIVE periods
+ * m = slot*W + j and, of each, the samples n = part, part+L, ...; one walk over the twiddle
+ * table gives it the three segment sums of each of its periods (acc[j][c], c = 0..2: each sample
+ * is multiplied once, whatever the number of candidates).  Window w of a candidate that starts
+ * `rho_c` into the periods is then
+ *      tail segments (>= c) of period w + shift,  plus
+ *      head segments (<  c) of period w + shift + 1, rotated by the tones' phase advance over
+ *      one period (geom.rot; the correlation phase restarts at every period),
+ * the second half coming from the next lane for the last of a lane's periods (shift = -1: the
+ * first half comes from the previous lane instead).  The magnitude of that sum is the reference's
+ * |X_k| of the window (src/fsk.c:157-159) up to a unit phase factor.  Periods n_bits (heads only)
+ * and -1 (tails only, for candidates before the anchor) take the slots after the last window;
+ * when only one is free they share it (mbatch.csplit). */
+template <int W>
+struct LaneWinM {
+    unsigned beg[W];	/* ring distance of period j from the anchor (0 for a slot past the last period) */
+    unsigned own;	/* bit j: this lane decides window j (one of the L lanes of the slot, round-robin) */
+    unsigned exp;	/* 2 bits per (sel, j): expect value 0, 1 or 2 */
+    unsigned wrapj;	/* the j whose slot is the wrap-around slot (period -1), W if it is not this lane's */
+};
+
+template <int G, int W, int L>
+__device__ __forceinline__ LaneWinM<W> lane_windows_multi(const fsk_b200_geom &geo, unsigned g)
+{
+    constexpr unsigned SLOTS = (unsigned)(W * (G / L));
+    const unsigned part = g % L, slot = g / L;
+    LaneWinM<W> lw;
+    lw.own = 0;
+    lw.exp = 0;
+    lw.wrapj = W;
+#pragma unroll
+    for (int j = 0; j < W; j++) {
+	const unsigned m = slot * W + j;
+	const bool window = m < geo.n_bits, period = m <= geo.n_bits;
+	lw.beg[j] = period ? geo.bit_nsamples * m : 0u;
+	if (window && part == (unsigned)(j % L))
+	    lw.own |= 1u << j;
+	const unsigned e0 = window ? geo.expect[0][m] : 2u, e1 = window ? geo.expect[1][m] : 2u;
+	lw.exp |= (e0 << (2 * j)) | (e1 << (2 * (j + W)));
+	if (m == SLOTS - 1u)
+	    lw.wrapj = j;
+    }
+    return lw;
+}
+
+/* segment sums of this lane's W periods: one pass over the period, the accumulator set switching
+ * at rho1 and rho2 (the loop variable simply runs on, so every lane keeps its n = part mod L) */
+template <int W, int L>
+__device__ __forceinline__ void corr_multi(float (&acc)[W][3][4], const float *const (&p0)[W],
+	const float *const (&p1)[W], const float *const (&p2)[W], const float4 *tw, unsigned part,
+	unsigned rho1, unsigned rho2, unsigned N)
+{
+    unsigned n = part;
+#define FSK_SEG_LOOP(C, PTR, END) \
+    _Pragma("unroll 4") \
+    for (; n < (END); n += L) { \
+	const float4 c = tw[n]; \
+	_Pragma("unroll") \
+	for (int j = 0; j < W; j++) { \
+	    const float x = PTR[j][n]; \
+	    acc[j][C][0] = fmaf(x, c.x, acc[j][C][0]); \
+	    acc[j][C][1] = fmaf(x, c.y, acc[j][C][1]); \
+	    acc[j][C][2] = fmaf(x, c.z, acc[j][C][2]); \
+	    acc[j][C][3] = fmaf(x, c.w, acc[j][C][3]); \
+	} \
+    }
+    FSK_SEG_LOOP(0, p0, rho1)
+    FSK_SEG_LOOP(1, p1, rho2)
+    FSK_SEG_LOOP(2, p2, N)
+#undef FSK_SEG_LOOP
+}
+
+/* (a + ib) * (c + is) added to (x + iy) */
+__device__ __forceinline__ void rot_add(float &x, float &y, float a, float b, float c, float s)
+{
+    x += fmaf(c, a, -(s * b));
+    y += fmaf(c, b, s * a);
+}
+
+/* one search of the rx loop (src/fsk.c:449-538 as called at src/minimodem.c:1265 / :1373), all of
+ * its candidates from shared segment sums */
+template <int G, int W, int L>
+__device__ __forceinline__ Found find_frame_multi(const Ring rg, unsigned pos_off,
+	const fsk_b200_geom &geo, const LaneWinM<W> &lw, int sel, unsigned tw_s, unsigned g, unsigned gmask,
+	const fsk_b200_mkind &kind, float limit, bool pending, unsigned &ncand)
+{
+    const float *ring = static_cast<const float *>(__cvta_shared_to_generic(rg.ring_s));
+    const float4 *tw = static_cast<const float4 *>(__cvta_shared_to_generic(tw_s));
+    const unsigned N = geo.bit_nsamples, R = rg.R;
+    const unsigned part = g % L;
+    Found best = { 0.f, 0.f, 0u, 0u, 0u };
+    unsigned best_order = 0;
+
+    for (unsigned b = 0; b < kind.nbatch; b++) {
+	const fsk_b200_mbatch &mb = kind.b[b];
+	const unsigned anchor_off = ring_wrap(pos_off + mb.anchor, R);
+	/* period pointers; the wrap-around slot reads its segments >= csplit one grid length
+	 * (SLOTS periods) earlier, which is the period before the anchor */
+	const float *p0[W], *p1[W], *p2[W];
+#pragma unroll
+	for (int j = 0; j < W; j++) {
+	    const float *fwd = ring + ring_wrap(anchor_off + lw.beg[j], R);
+	    p0[j] = p1[j] = p2[j] = fwd;
+	    if ((unsigned)j == lw.wrapj && mb.csplit < 3u) {
+		const float *back = ring + (anchor_off >= N ? anchor_off - N : anchor_off + R - N);
+		if (mb.csplit <= 0u) p0[j] = back;
+		if (mb.csplit <= 1u) p1[j] = back;
+		p2[j] = back;
+	    }
+	}
+	float acc[W][3][4];
+#pragma unroll
+	for (int j = 0; j < W; j++)
+#pragma unroll
+	    for (int c = 0; c < 3; c++)
+		acc[j][c][0] = acc[j][c][1] = acc[j][c][2] = acc[j][c][3] = 0.f;
+	if (pending) {			/* the copies of this iteration: waited for as late as possible */
+	    cp_async_wait<0>();
+	    __syncwarp(gmask);
+	    pending = false;
+	}
+	corr_multi<W, L>(acc, p0, p1, p2, tw, part, mb.rho1, mb.rho2, N);
+
+	for (unsigned i = 0; i < mb.ncand; i++) {
+	    const unsigned cs = mb.cseg[i];
+	    const int shift = mb.shift[i];
+	    const unsigned t = mb.t[i];
+	    ncand++;
+	    /* this lane's partial sums of its W windows */
+	    float wp[W][4];
+	    if (cs == 0u && shift == 0) {
+		/* the windows are whole periods */
+#pragma unroll
+		for (int j = 0; j < W; j++)
+#pragma unroll
+		    for (int k = 0; k < 4; k++)
+			wp[j][k] = (acc[j][0][k] + acc[j][1][k]) + acc[j][2][k];
+	    } else {
+		/* tails (segments >= cs) and heads (segments < cs) of every period of this lane */
+		float tl[W][4], hd[W][4];
+#pragma unroll
+		for (int j = 0; j < W; j++)
+#pragma unroll
+		    for (int k = 0; k < 4; k++) {
+			if (cs == 0u) {			/* shift = +1: the whole NEXT period */
+			    tl[j][k] = 0.f;
+			    hd[j][k] = (acc[j][0][k] + acc[j][1][k]) + acc[j][2][k];
+			} else if (cs == 1u) {
+			    tl[j][k] = acc[j][1][k] + acc[j][2][k];
+			    hd[j][k] = acc[j][0][k];
+			} else {
+			    tl[j][k] = acc[j][2][k];
+			    hd[j][k] = acc[j][0][k] + acc[j][1][k];
+			}
+		    }
+		if (shift >= 0) {
+		    /* window j = tail of period j + head of period j+1 (the next lane's first for j = W-1) */
+		    float nx[4];
+#pragma unroll
+		    for (int k = 0; k < 4; k++)
+			nx[k] = __shfl_sync(gmask, hd[0][k], (g + L) & (G - 1), G);
+#pragma unroll
+		    for (int j = 0; j < W; j++) {
+			const float h0 = j + 1 < W ? hd[j + 1 < W ? j + 1 : 0][0] : nx[0];
+			const float h1 = j + 1 < W ? hd[j + 1 < W ? j + 1 : 0][1] : nx[1];
+			const float h2 = j + 1 < W ? hd[j + 1 < W ? j + 1 : 0][2] : nx[2];
+			const float h3 = j + 1 < W ? hd[j + 1 < W ? j + 1 : 0][3] : nx[3];
+			wp[j][0] = tl[j][0]; wp[j][1] = tl[j][1]; wp[j][2] = tl[j][2]; wp[j][3] = tl[j][3];
+			rot_add(wp[j][0], wp[j][1], h0, h1, geo.rot[0], geo.rot[1]);
+			rot_add(wp[j][2], wp[j][3], h2, h3, geo.rot[2], geo.rot[3]);
+		    }
+		} else {
+		    /* shift = -1: window j = tail of period j-1 (the previous lane's last for j = 0) + head of period j */
+		    float pv[4];
+#pragma unroll
+		    for (int k = 0; k < 4; k++)
+			pv[k] = __shfl_sync(gmask, tl[W - 1][k], (g + G - L) & (G - 1), G);
+#pragma unroll
+		    for (int j = 0; j < W; j++) {
+#pragma unroll
+			for (int k = 0; k < 4; k++)
+			    wp[j][k] = j > 0 ? tl[j > 0 ? j - 1 : 0][k] : pv[k];
+			rot_add(wp[j][0], wp[j][1], hd[j][0], hd[j][1], geo.rot[0], geo.rot[1]);
+			rot_add(wp[j][2], wp[j][3], hd[j][2], hd[j][3], geo.rot[2], geo.rot[3]);
+		    }
+		}
+	    }
+	    /* first sample of this lane's windows (fp64 re-sum of near-zero bins only) */
+	    const float *q[W];
+	    const unsigned cand_off = ring_wrap(pos_off + t, R);
+#pragma unroll
+	    for (int j = 0; j < W; j++)
+		q[j] = ring + ring_wrap(cand_off + lw.beg[j], R);
+	    unsigned lo, hi;
+	    float a;
+	    const float c = frame_finish<G, W, L, false, true>(wp, q, lw.own, lw.exp, geo, tw, sel, g, gmask,
+		    lo, hi, a);
+	    /* src/fsk.c:492-501 visits the candidates in `order`; a later batch may hold an earlier
+	     * candidate, so among equals the earlier one is kept (what `best_c < c` does there) */
+	    const unsigned order = mb.order[i];
+	    if (best.confidence < c || (best.confidence == c && c > 0.f && order < best_order)) {
+		best = Found{ c, a, t, lo, hi };
+		best_order = order;
+		if (c >= limit && kind.nbatch == 1u)
+		    return best;			/* first to reach the limit wins (:499) */
+	    }
+	}
+    }
+    return best;
+}
 /* ------------------------------------------------------------------------ */
 /* asynchronous ring fill: HBM -> shared memory, 16 bytes per cp.async,     */
 /* every sample fetched once; bytes at or past the valid length arrive as 0 */

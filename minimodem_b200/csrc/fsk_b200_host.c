@@ -311,6 +311,170 @@ int fsk_b200_rx_params_derive(const fsk_b200_rx_config *cfg, fsk_b200_rx_params 
     return 0;
 }
 
+/* ------------------------------------------------------------------------ */
+/* shared-segment search plan (fsk_b200_internal.h)                          */
+/* ------------------------------------------------------------------------ */
+
+struct cand { int t; unsigned order; };
+
+/* the visiting order of src/fsk.c:477-484 */
+static unsigned enumerate_candidates(unsigned first, unsigned tmax, unsigned step, struct cand *c, unsigned cap)
+{
+    unsigned n = 0, order = 0;
+    if (step == 0)
+	step = 1;
+    for (int j = 0;; j++) {
+	const int up = (j & 1) ? 1 : -1;
+	const int t = (int)first + up * ((j + 1) / 2) * (int)step;
+	if (t >= (int)tmax)
+	    break;
+	if (t < 0) {
+	    if (j > 4 * (int)tmax + 8)
+		break;			/* cannot happen: the upward side ends the scan */
+	    continue;
+	}
+	if (n == cap)
+	    return cap + 1;
+	c[n].t = t;
+	c[n].order = order++;
+	n++;
+    }
+    return n;
+}
+
+/* one batch over candidates c[0..n) (n <= 3) anchored at `anchor`; -1 if they do not fit the scheme */
+static int plan_batch(const struct cand *c, unsigned n, int anchor, unsigned N, unsigned n_bits,
+	unsigned slots, fsk_b200_mbatch *b)
+{
+    memset(b, 0, sizeof(*b));
+    int r[3], d[3];
+    unsigned rho[3] = { 0, 0, 0 }, nrho = 1;
+    for (unsigned i = 0; i < n; i++) {
+	const int off = c[i].t - anchor;
+	d[i] = off >= 0 ? off / (int)N : -((-off + (int)N - 1) / (int)N);
+	r[i] = off - d[i] * (int)N;
+	if (d[i] == 1 && r[i] != 0)
+	    return -1;
+	if (d[i] == -1 && r[i] == 0)
+	    return -1;
+	if (d[i] < -1 || d[i] > 1)
+	    return -1;
+	unsigned k;
+	for (k = 0; k < nrho; k++)
+	    if (rho[k] == (unsigned)r[i])
+		break;
+	if (k == nrho) {
+	    if (nrho == 3)
+		return -1;
+	    rho[nrho++] = (unsigned)r[i];
+	}
+    }
+    /* sort the residues; rho[0] = 0 is the smallest by construction */
+    if (nrho == 3 && rho[1] > rho[2]) { unsigned x = rho[1]; rho[1] = rho[2]; rho[2] = x; }
+    b->anchor = (uint16_t)anchor;
+    b->rho1 = (uint16_t)(nrho > 1 ? rho[1] : N);
+    b->rho2 = (uint16_t)(nrho > 2 ? rho[2] : N);
+    b->ncand = (uint8_t)n;
+    unsigned max_fwd = 0, min_back = 3, need_last_full = 0, any_back = 0;
+    for (unsigned i = 0; i < n; i++) {
+	unsigned k;
+	for (k = 0; k < nrho; k++)
+	    if (rho[k] == (unsigned)r[i])
+		break;
+	b->t[i] = (uint16_t)c[i].t;
+	b->cseg[i] = (uint8_t)k;
+	b->shift[i] = (int8_t)d[i];
+	b->order[i] = (uint8_t)c[i].order;
+	if (d[i] == 0 && k > max_fwd)
+	    max_fwd = k;		/* reads segments < k of period n_bits */
+	if (d[i] == 1)
+	    need_last_full = 1;		/* reads all of period n_bits */
+	if (d[i] == -1) {
+	    any_back = 1;
+	    if (k < min_back)
+		min_back = k;		/* reads segments >= k of period -1 */
+	}
+    }
+    /* periods 0..n_bits need a slot each; period -1 lives in the last slot (wrap-around) */
+    if (slots < n_bits + 1u)
+	return -1;
+    b->csplit = 3;
+    if (any_back) {
+	if (slots - 1u > n_bits)
+	    b->csplit = 0;			/* a slot of its own */
+	else if (!need_last_full && max_fwd <= min_back)
+	    b->csplit = (uint8_t)min_back;	/* shared with period n_bits: disjoint segments */
+	else
+	    return -1;
+    }
+    return 0;
+}
+
+int fsk_b200_mplan_build(const fsk_b200_geom *g, const fsk_b200_loopc *lc, unsigned int slots,
+	fsk_b200_mplan *out)
+{
+    memset(out, 0, sizeof(*out));
+    const unsigned N = g->bit_nsamples;
+    if (N < 2 || N > 0xfff0u || g->n_bits > 32)
+	return -1;
+    for (unsigned w = 0; w < g->n_bits; w++)
+	if (g->bit_begin[w] != w * N)
+	    return -1;				/* the bit windows do not tile */
+    for (int kind = 0; kind < 4; kind++) {
+	const int carrier = kind & 1, fine = kind >> 1;
+	const unsigned tmax = carrier ? lc->try_max_carrier : lc->try_max_nocarrier;	/* src/minimodem.c:1236-1241 */
+	const unsigned first = carrier ? lc->nsamples_overscan : 0u;			/* :1263 */
+	unsigned step = tmax / 3u;							/* :1248-1251 */
+	if (step == 0)
+	    step = 1;
+	if (tmax > 0xfff0u)
+	    return -1;
+	if (fine) {
+	    if (step <= 1u) {			/* :1357: no fine search in this mode */
+		out->kind[kind].nbatch = 0;
+		continue;
+	    }
+	    step = tmax / 8u;								/* :1360-1362 */
+	    if (step == 0)
+		step = 1;
+	}
+	struct cand c[3 * FSK_MULTI_MAXB];
+	const unsigned n = enumerate_candidates(first, tmax, step, c, 3 * FSK_MULTI_MAXB);
+	if (n == 0 || n > 3 * FSK_MULTI_MAXB)
+	    return -1;
+	fsk_b200_mkind *k = &out->kind[kind];
+	if (!fine) {
+	    /* one batch, anchored at the candidate visited first: in the steady state that one wins
+	     * (src/fsk.c:499) and it is the cheapest to evaluate (its windows are whole periods) */
+	    if (n > 3 || plan_batch(c, n, c[0].t, N, g->n_bits, slots, &k->b[0]) != 0)
+		return -1;
+	    k->nbatch = 1;
+	} else {
+	    /* sorted by offset, three neighbours per batch, anchored at the smallest */
+	    for (unsigned i = 1; i < n; i++)
+		for (unsigned j = i; j > 0 && c[j].t < c[j - 1].t; j--) {
+		    struct cand x = c[j]; c[j] = c[j - 1]; c[j - 1] = x;
+		}
+	    unsigned nb = 0;
+	    for (unsigned i = 0; i < n; i += 3, nb++) {
+		const unsigned m = n - i < 3 ? n - i : 3;
+		/* inside a batch the kernel keeps the visiting order */
+		struct cand bc[3];
+		for (unsigned q = 0; q < m; q++)
+		    bc[q] = c[i + q];
+		for (unsigned q = 1; q < m; q++)
+		    for (unsigned j = q; j > 0 && bc[j].order < bc[j - 1].order; j--) {
+			struct cand x = bc[j]; bc[j] = bc[j - 1]; bc[j - 1] = x;
+		    }
+		if (nb == FSK_MULTI_MAXB || plan_batch(bc, m, c[i].t, N, g->n_bits, slots, &k->b[nb]) != 0)
+		    return -1;
+	    }
+	    k->nbatch = nb;
+	}
+    }
+    return 0;
+}
+
 uint32_t fsk_b200_max_frames(const fsk_b200_rx_params *p, uint32_t nsamples)
 {
     /* every recorded frame advances by at least frame_nsamples - overscan (:1407);
@@ -371,6 +535,15 @@ fsk_b200_engine *fsk_b200_engine_new(const fsk_b200_rx_params *params)
 	fsk_b200_set_error("engine_new: bad frame geometry");
 	errno = EINVAL;
 	return NULL;
+    }
+    {	/* phase advance of the two tones over one bit period, argument reduced exactly in integers */
+	const unsigned long long F = (unsigned long long)(params->fftsize > 0 ? params->fftsize : 1);
+	const double am = 2.0 * M_PI * (double)(((unsigned long long)params->b_mark * e->geom.bit_nsamples) % F) / (double)F;
+	const double as = 2.0 * M_PI * (double)(((unsigned long long)params->b_space * e->geom.bit_nsamples) % F) / (double)F;
+	e->geom.rot[0] = (float)cos(am);
+	e->geom.rot[1] = (float)-sin(am);
+	e->geom.rot[2] = (float)cos(as);
+	e->geom.rot[3] = (float)-sin(as);
     }
     e->loopc.frame_nsamples = params->frame_nsamples;
     e->loopc.expect_nsamples = params->expect_nsamples;

@@ -22,16 +22,54 @@ typedef struct fsk_b200_geom {
     float	mag_scalar;		/* 2.0f / bit_nsamples, src/fsk.c:132 */
     float	eps_unscaled;		/* FLT_EPSILON / mag_scalar: the :279 threshold before scaling */
     float	inv_n_bits;		/* 1.0f / n_bits */
+    float	rot[4];			/* exp(-2 pi i b N / fftsize) for b = b_mark, b_space as (re, im), N = bit_nsamples:
+					 * the phase step from one bit period to the next (shared-segment search) */
     unsigned int bit_begin[FSK_B200_MAX_BITS];
     unsigned char expect[2][FSK_B200_MAX_BITS];	/* [0]=data [1]=sync; 0,1 or 2 ('d') */
 } fsk_b200_geom;
 
 /* rx-loop constants for the rx kernel (by value as well) */
+struct fsk_b200_loopc;
 typedef struct fsk_b200_loopc {
     unsigned int frame_nsamples, expect_nsamples, nsamples_overscan;
     unsigned int try_max_nocarrier, try_max_carrier;
     float	confidence_threshold, confidence_search_limit;
 } fsk_b200_loopc;
+
+/* ---- shared-segment search plan (the "multi" rx kernel) --------------------------------------
+ * When the bit windows of a frame candidate tile (bit_begin[w] == w * bit_nsamples, i.e.
+ * expect_nsamples divisible by the number of expected bits: Bell202 1200, Bell103 300, RTTY 45.45 at
+ * 8 and 48 kHz ...), all candidates of one fsk_find_frame call (src/fsk.c:477-502) read the same
+ * samples cut at different places.  A BATCH of up to three candidates lays one grid of bit periods
+ * over them, anchored at one candidate, and cuts every period at the (at most two) offsets where
+ * the other candidates' windows begin: each sample is then correlated ONCE, into the sum of its
+ * segment, and a window of any candidate of the batch is the sum of the tail segments of one period
+ * and the head segments of the next (rotated by the tones' phase advance over one period, geom.rot).
+ * A coarse search (try_step = try_max/3) is one batch; a fine search (try_max/8) is up to four. */
+#define FSK_MULTI_MAXB 4
+typedef struct fsk_b200_mbatch {
+    uint16_t	anchor;		/* try offset the period grid is anchored at */
+    uint16_t	rho1, rho2;	/* a period is cut into [0,rho1) [rho1,rho2) [rho2,N); segments may be empty */
+    uint16_t	t[3];		/* candidate try offsets, in the order fsk_find_frame visits them */
+    uint8_t	ncand;		/* 1..3 */
+    uint8_t	csplit;		/* wrap-around slot: its segments >= csplit belong to the period BEFORE the anchor (3 = none) */
+    uint8_t	cseg[3];	/* first segment of candidate i's windows (0 = it starts where a period starts) */
+    int8_t	shift[3];	/* period that window w of candidate i starts in, minus w: -1, 0 or +1 */
+    uint8_t	order[3];	/* index of candidate i in the whole search's visiting order */
+    uint8_t	pad;
+} fsk_b200_mbatch;
+typedef struct fsk_b200_mkind {
+    uint32_t	nbatch;
+    fsk_b200_mbatch b[FSK_MULTI_MAXB];
+} fsk_b200_mkind;
+/* search kinds of the rx loop: [carrier + 2 * fine]; the fine search of the iteration that ACQUIRES
+ * the carrier still uses the no-carrier window (src/minimodem.c:1236-1263 are evaluated before :1357) */
+typedef struct fsk_b200_mplan {
+    fsk_b200_mkind kind[4];
+} fsk_b200_mplan;
+/* 0 and the plan if every search kind of this mode can run on `slots` period slots, else -1 */
+int fsk_b200_mplan_build(const fsk_b200_geom *g, const struct fsk_b200_loopc *lc, unsigned int slots,
+	fsk_b200_mplan *out);
 
 void fsk_b200_set_error(const char *fmt, ...);
 

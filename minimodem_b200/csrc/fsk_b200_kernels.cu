@@ -204,14 +204,16 @@ template <int G, int W, int L, int MODE, int FILL>
 __global__ void __launch_bounds__(FSK_MAXTHREADS, FSK_MINBLOCKS)
 k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200_loopc lc,
 	const float4 *__restrict__ tw_global, unsigned tw_in_smem, unsigned ring_floats,
-	unsigned lookahead, const __grid_constant__ RxArgs a)
+	unsigned lookahead, const __grid_constant__ RxArgs a, const __grid_constant__ fsk_b200_mplan mp)
 {
     FSK_DYN_SMEM(smem4);
     const Smem sm = carve<G>(smem4, geo, tw_global, tw_in_smem, ring_floats);
     GROUP_VARS;
     const Ring rg = { smem_u32(sm.ring), ring_floats, (geo.bit_nsamples + 3u) & ~3u };
     const unsigned tw_s = tw_in_smem ? smem_u32(sm.tw) : 0u;	/* the fast path requires the table in shared memory */
+    /* MODE 2 (shared-segment search) owns CONSECUTIVE bit periods per lane, MODE 0 interleaved windows */
     const LaneWin<W> lw = lane_windows<G, W, L>(geo, g);
+    const LaneWinM<W> lwm = lane_windows_multi<G, W, L>(geo, g);
     const unsigned R = ring_floats;
 
     for (unsigned s = (blockIdx.x * wpb + warp) * spw + sidx; s < a.nstreams;
@@ -329,7 +331,7 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
 	    }
 	    __syncwarp(gmask);
 	};
-	if (MODE == 0) {
+	if (MODE != 1) {
 	    if (FILL == 1) {
 		if (g == 0) {
 		    mbar_init(bar0, 1);
@@ -357,7 +359,7 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
 
 	    int ready = 0;
 	    bool pending = false;
-	    if (MODE == 0) {
+	    if (MODE != 1) {
 		/* The samples of this iteration were normally requested an iteration ago (EARLY_REQ,
 		 * below); whatever is missing -- first iteration of a launch, a restarted ring, the
 		 * bulk variant -- is requested here together with what the next iteration can need
@@ -388,7 +390,7 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
 	    float amplitude, confidence;
 	    unsigned frame_start;
 	    Found refined = { 0.f, 0.f, 0u, 0u, 0u };
-	    if (MODE == 0) {
+	    if (MODE != 1) {
 		/* one (inlined) search site, taken a second time for the refinement of :1357-1389: whether
 		 * that happens is a pure function of the first result and the loop state, so it is
 		 * decided here and the state machine below only merges the outcome */
@@ -398,8 +400,13 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
 		int which = sel;
 		for (int pass = 0;; pass++) {
 		    nsearch++;
-		    const Found f = find_frame_fast_body<G, W, L>(rg, pos_off, geo, lw, which, tw_s, g,
-			    gmask, try_first, try_max, step, limit, ready, pending, ncand);	/* :1265, :1378 */
+		    /* :1265, :1378.  MODE 2: all candidates of the search from shared segment sums; which plan:
+		     * the window is the one chosen at the top of the iteration (carrier then), coarse or fine */
+		    const Found f = MODE == 2
+			? find_frame_multi<G, W, L>(rg, pos_off, geo, lwm, which, tw_s, g, gmask,
+				mp.kind[(carrier ? 1 : 0) + (pass ? 2 : 0)], limit, pending, ncand)
+			: find_frame_fast_body<G, W, L>(rg, pos_off, geo, lw, which, tw_s, g,
+				gmask, try_first, try_max, step, limit, ready, pending, ncand);
 		    if (pass) {
 			refined = f;
 			break;
@@ -519,7 +526,7 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
 	    }
 	    if (advance > remaining) { done = 1; break; }	/* :1151 */
 	    pos += advance;
-	    if (MODE == 0) {
+	    if (MODE != 1) {
 		pos_off = ring_wrap(pos_off + advance, R);	/* advance < R by construction */
 		if (filled < (pos & ~3u)) {
 		    /* skipped past everything requested so far: restart the ring here */
@@ -533,7 +540,7 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
 		__syncwarp(gmask);	/* every read of this window precedes the next copies */
 	    }
 	}
-	if (MODE == 0)
+	if (MODE != 1)
 	    drain();	/* before the slot is reused or the block exits */
 
 	if (g == 0) {

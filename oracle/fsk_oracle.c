@@ -4,6 +4,7 @@
  * product.  Citations are path:line under /root/reference/.
  */
 #define _GNU_SOURCE
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <math.h>
@@ -703,22 +704,70 @@ struct orc_pool {
     unsigned long long *bits_xor;
 };
 
+/* Pinning order: the allowed CPUs sorted so that one hardware thread of every physical core comes
+ * first (sockets alternating), the cores' second hardware threads after them -- N workers then
+ * occupy min(N, cores) distinct cores whatever the kernel's CPU numbering is (siblings adjacent,
+ * or all first threads before all second ones).  ORC_POOL_PIN=none leaves the scheduler alone,
+ * ORC_POOL_PIN=compact takes the allowed CPUs in numeric order. */
+static int pool_cpu_order(int *order, int cap)
+{
+    cpu_set_t allowed;
+    if (sched_getaffinity(0, sizeof(allowed), &allowed) != 0)
+	return 0;
+    struct { int cpu, pkg, core; } c[CPU_SETSIZE];
+    int n = 0;
+    for (int cpu = 0; cpu < CPU_SETSIZE && n < cap; cpu++) {
+	if (!CPU_ISSET(cpu, &allowed))
+	    continue;
+	char path[128];
+	int pkg = 0, core = cpu;
+	FILE *f;
+	snprintf(path, sizeof(path), "/sys/devices/system/cpu/cpu%d/topology/physical_package_id", cpu);
+	if ((f = fopen(path, "r"))) { if (fscanf(f, "%d", &pkg) != 1) pkg = 0; fclose(f); }
+	snprintf(path, sizeof(path), "/sys/devices/system/cpu/cpu%d/topology/core_id", cpu);
+	if ((f = fopen(path, "r"))) { if (fscanf(f, "%d", &core) != 1) core = cpu; fclose(f); }
+	c[n].cpu = cpu; c[n].pkg = pkg; c[n].core = core;
+	n++;
+    }
+    const char *mode = getenv("ORC_POOL_PIN");
+    if (mode && strcmp(mode, "compact") == 0) {
+	for (int i = 0; i < n; i++)
+	    order[i] = c[i].cpu;
+	return n;
+    }
+    /* rank of a CPU among the hardware threads of its core (0 = first thread) */
+    int rank[CPU_SETSIZE];
+    for (int i = 0; i < n; i++) {
+	rank[i] = 0;
+	for (int j = 0; j < i; j++)
+	    if (c[j].pkg == c[i].pkg && c[j].core == c[i].core)
+		rank[i]++;
+    }
+    int k = 0;
+    for (int r = 0; r < 8 && k < n; r++)
+	for (int i = 0; i < n; i++)
+	    if (rank[i] == r)
+		order[k++] = c[i].cpu;
+    return k;
+}
+
 static void pool_pin(int tid)
 {
-    cpu_set_t allowed, one;
-    if (sched_getaffinity(0, sizeof(allowed), &allowed) != 0)
+    const char *mode = getenv("ORC_POOL_PIN");
+    if (mode && strcmp(mode, "none") == 0)
 	return;
-    int ncpu = CPU_COUNT(&allowed), want = tid % (ncpu ? ncpu : 1), seen = 0;
-    for (int c = 0; c < CPU_SETSIZE; c++) {
-	if (!CPU_ISSET(c, &allowed))
-	    continue;
-	if (seen++ == want) {
-	    CPU_ZERO(&one);
-	    CPU_SET(c, &one);
-	    pthread_setaffinity_np(pthread_self(), sizeof(one), &one);
-	    return;
-	}
-    }
+    static int order[CPU_SETSIZE], norder = -1;
+    static pthread_mutex_t mu = PTHREAD_MUTEX_INITIALIZER;
+    pthread_mutex_lock(&mu);
+    if (norder < 0)
+	norder = pool_cpu_order(order, CPU_SETSIZE);
+    pthread_mutex_unlock(&mu);
+    if (norder <= 0)
+	return;
+    cpu_set_t one;
+    CPU_ZERO(&one);
+    CPU_SET(order[tid % norder], &one);
+    pthread_setaffinity_np(pthread_self(), sizeof(one), &one);
 }
 
 static void *pool_worker_main(void *arg)
