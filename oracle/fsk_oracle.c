@@ -756,12 +756,8 @@ static void pool_pin(int tid)
     const char *mode = getenv("ORC_POOL_PIN");
     if (mode && strcmp(mode, "none") == 0)
 	return;
-    static int order[CPU_SETSIZE], norder = -1;
-    static pthread_mutex_t mu = PTHREAD_MUTEX_INITIALIZER;
-    pthread_mutex_lock(&mu);
-    if (norder < 0)
-	norder = pool_cpu_order(order, CPU_SETSIZE);
-    pthread_mutex_unlock(&mu);
+    int order[CPU_SETSIZE];
+    const int norder = pool_cpu_order(order, CPU_SETSIZE);
     if (norder <= 0)
 	return;
     cpu_set_t one;
