@@ -377,6 +377,10 @@ int fsk_b200_tx_batch(const fsk_b200_tx_config *cfg, const float *sin_table, uin
 	const uint32_t *words, uint32_t nwords, const uint32_t *lead_in,
 	float *samples_out, size_t nstreams, size_t stride, uint32_t nsamples_out, void *stream);
 
+/* Diagnostics: which rx kernel the engine's latest fsk_b200_rx_batch launched ("k_rx<G=8,W=3,L=2,mode=2
+ * (shared-segment),fill=0> threads=64 ring=640 smem=23232 blocks=8192"; "" before the first launch). */
+const char *fsk_b200_engine_last_kernel(const fsk_b200_engine *e);
+
 /* Library / build information: "fsk_b200 <version> sm_100a". */
 const char *fsk_b200_version(void);
 /* Number of kernel launches issued by this library in this process. */

@@ -103,7 +103,7 @@ EXPORTS = [
     "fsk_b200_decode_batch", "fsk_b200_decoder_for_mode", "fsk_b200_decode_max_bytes_per_frame",
     "fsk_b200_decode_max_bytes", "fsk_b200_detect_carrier_batch",
     "fsk_b200_stream_window", "fsk_b200_engine_set_holdback", "fsk_b200_stream_push", "fsk_b200_wav_locate",
-    "fsk_b200_version", "fsk_b200_launch_count", "fsk_b200_last_error",
+    "fsk_b200_version", "fsk_b200_launch_count", "fsk_b200_last_error", "fsk_b200_engine_last_kernel",
 ]
 
 _lib = None
@@ -157,6 +157,8 @@ def lib():
     L.fsk_b200_engine_destroy.restype = None
     L.fsk_b200_engine_params.argtypes = [C.c_void_p]
     L.fsk_b200_engine_params.restype = C.POINTER(RxParams)
+    L.fsk_b200_engine_last_kernel.argtypes = [C.c_void_p]
+    L.fsk_b200_engine_last_kernel.restype = C.c_char_p
     L.fsk_b200_engine_tune.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
     L.fsk_b200_engine_tune.restype = C.c_int
     L.fsk_b200_find_frame_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, u32p, u32p,
@@ -352,6 +354,10 @@ class RxEngine:
         rc = lib().fsk_b200_engine_tune(self._e, lanes_per_stream, warps_per_block, ring_floats)
         if rc:
             _err("fsk_b200_engine_tune", rc)
+
+    def last_kernel(self):
+        """Which rx kernel the latest rx_batch launched (diagnostics)."""
+        return lib().fsk_b200_engine_last_kernel(self._e).decode()
 
     def max_frames(self, nsamples):
         return max_frames(self.params, nsamples)

@@ -564,6 +564,11 @@ fsk_b200_engine *fsk_b200_engine_new(const fsk_b200_rx_params *params)
     return e;
 }
 
+const char *fsk_b200_engine_last_kernel(const fsk_b200_engine *e)
+{
+    return e ? fsk_b200_cuda_last_kernel(e->ce) : "";
+}
+
 void fsk_b200_engine_destroy(fsk_b200_engine *e)
 {
     if (!e)

@@ -84,6 +84,7 @@ void fsk_b200_cuda_engine_destroy(void *ce);
 /* (re)build the twiddle table for (fftsize, b_mark, b_space, bit_nsamples) */
 int  fsk_b200_cuda_set_table(void *ce, int fftsize, unsigned int b_mark, unsigned int b_space,
 	unsigned int bit_nsamples);
+const char *fsk_b200_cuda_last_kernel(void *ce);
 int  fsk_b200_cuda_tune(void *ce, int lanes_per_stream, int warps_per_block, int ring_floats);
 int  fsk_b200_cuda_find_frame_batch(void *ce, const fsk_b200_geom *g, const float *samples,
 	size_t nstreams, size_t stride, const uint32_t *offset, const uint32_t *nvalid,

@@ -1038,6 +1038,8 @@ struct CudaEngine {
     unsigned tw_bm, tw_bs;
     /* tuning (0 = automatic) */
     int lanes, wpb, ring, split, fill;
+    char last_kernel[160];	/* what the latest rx / find_frame launch ran (diagnostics) */
+    int multi;			/* 1 (default): shared-segment search where the mode allows it; 0: always per candidate */
     /* single-stream staging */
     float *d_one;
     size_t d_one_cap;
@@ -1086,6 +1088,8 @@ extern "C" void *fsk_b200_cuda_engine_new(void)
     if ((e = getenv("FSK_B200_SPLIT"))) ce->split = atoi(e);
     ce->fill = 0;		/* see the dispatch in fsk_b200_cuda_rx_batch */
     if ((e = getenv("FSK_B200_FILL"))) ce->fill = atoi(e);
+    ce->multi = 1;
+    if ((e = getenv("FSK_B200_MULTI"))) ce->multi = atoi(e);
     /* 256 MiB of samples ON THE WIRE per slab, two slabs in flight: the float path runs at the PCIe
      * rate with that (54 GB/s).  The int16 path, measured with slabs of the same stream count (128 MiB
      * on the wire), reached 78 % of it -- about 0.7 ms per slab stayed exposed (one conversion plus
@@ -1129,6 +1133,8 @@ extern "C" void fsk_b200_cuda_engine_destroy(void *p)
     }
     free(ce);
 }
+
+extern "C" const char *fsk_b200_cuda_last_kernel(void *p) { return ((CudaEngine *)p)->last_kernel; }
 
 extern "C" int fsk_b200_cuda_tune(void *p, int lanes, int wpb, int ring)
 {
@@ -1210,6 +1216,7 @@ struct Shape {
     unsigned ring, tw_in_smem, lookahead;
     size_t smem;
     fsk_b200_geom geo;
+    fsk_b200_mplan mplan;	/* mode 2 */
 };
 
 /* (G, W, L) combinations that are instantiated for the fast path: G lanes per
@@ -1225,6 +1232,11 @@ struct Shape {
     X(32, 1, 1) X(32, 2, 1) X(32, 1, 2) X(32, 2, 2) X(32, 3, 2) X(32, 4, 2) X(32, 1, 4) X(32, 2, 4) X(32, 3, 4) X(32, 4, 4)
 #endif
 
+/* (G, W, L) of the shared-segment rx kernel (mode 2): W * G/L period slots >= n_bits + 1 */
+#define MULTI_COMBOS(X) \
+    X(8, 2, 2) X(8, 3, 2) X(8, 4, 2) X(16, 2, 2) X(16, 3, 2) X(16, 4, 2) X(16, 2, 4) X(16, 3, 4) X(16, 4, 4) \
+    X(32, 2, 4) X(32, 3, 4) X(32, 4, 4)
+
 /* the alternative kernels (TMA bulk fill, group-masked loop) are built for the shapes the
  * defaults pick for the BASELINE configurations only */
 #define ALT_COMBOS(X) X(8, 3, 2) X(8, 2, 2) X(16, 3, 4) X(16, 2, 4) X(16, 1, 2)
@@ -1235,6 +1247,17 @@ static bool fast_combo(int G, int W, int L)
     FAST_COMBOS(X)
 #undef X
     return false;
+}
+
+/* mode 2: the (W, L) of MULTI_COMBOS with the fewest idle period slots for `periods` bit periods */
+static bool split_for_multi(int G, unsigned periods, int *W, int *L)
+{
+    unsigned best = ~0u;
+#define X(GG, WW, LL) if (G == GG && (unsigned)(WW * (GG / LL)) >= periods && (unsigned)(WW * (GG / LL)) <= best) { \
+	best = (unsigned)(WW * (GG / LL)); *W = WW; *L = LL; }
+    MULTI_COMBOS(X)
+#undef X
+    return best != ~0u;
 }
 
 /* best (W, L) for a group of G lanes: highest lane utilisation n_bits / (W * G/L);
@@ -1261,9 +1284,10 @@ static bool split_for(int G, unsigned n_bits, int force_L, int *W, int *L)
 }
 
 static int pick_shape(const CudaEngine *ce, const fsk_b200_geom *g, unsigned need_floats,
-	unsigned max_advance, size_t nstreams, Shape *sh)
+	unsigned max_advance, size_t nstreams, Shape *sh, const fsk_b200_loopc *lc = NULL)
 {
     sh->geo = *g;
+    memset(&sh->mplan, 0, sizeof(sh->mplan));
     const size_t smem_max = (size_t)ce->smem_optin;
     const size_t tw_bytes = (size_t)g->bit_nsamples * sizeof(float4);
     sh->tw_in_smem = tw_bytes <= 24 * 1024;
@@ -1342,6 +1366,17 @@ static int pick_shape(const CudaEngine *ce, const fsk_b200_geom *g, unsigned nee
 	}
     }
     sh->mode = fast ? 0 : 1;
+    if (fast && lc && ce->multi && ce->fill == 0) {
+	/* the rx loop's searches from shared segment sums, if this mode's windows tile and all of its
+	 * searches fit the period slots of a (W, L) split of this group size */
+	int W2 = 0, L2 = 0;
+	if (split_for_multi(G, g->n_bits + 1u, &W2, &L2) && g->bit_nsamples <= FAST_MAX_N * (unsigned)L2
+		&& fsk_b200_mplan_build(g, lc, (unsigned)(W2 * (G / L2)), &sh->mplan) == 0) {
+	    sh->mode = 2;
+	    W = W2;
+	    L = L2;
+	}
+    }
     sh->G = G;
     sh->W = W;
     sh->L = L;
@@ -1433,7 +1468,7 @@ static cudaError_t launch_rx_t(const Shape &sh, const CudaEngine *ce, const fsk_
     if (e != cudaSuccess)
 	return e;
     FSK_LAUNCH((k_rx<G, W, L, MODE, FILL>), sh.blocks, sh.wpb * 32, sh.smem, st, sh.geo, *lc, ce->d_tw,
-	    sh.tw_in_smem, sh.ring, sh.lookahead, a);
+	    sh.tw_in_smem, sh.ring, sh.lookahead, a, sh.mplan);
     g_launches++;
     return cudaGetLastError();
 }
@@ -1454,12 +1489,16 @@ extern "C" int fsk_b200_cuda_rx_batch(void *p, const fsk_b200_geom *g, const fsk
     const unsigned tmax = lc->try_max_nocarrier > lc->try_max_carrier
 	? lc->try_max_nocarrier : lc->try_max_carrier;
     const unsigned max_advance = tmax - 1u + lc->frame_nsamples;	/* :1407, overscan >= 0 */
-    pick_shape(ce, g, tmax - 1u + g->span, max_advance, nstreams, &sh);
+    pick_shape(ce, g, tmax - 1u + g->span, max_advance, nstreams, &sh, lc);
     const RxArgs a = { samples, (unsigned)nstreams, stride, nsamples, nsamples_all, frames, max_frames,
 	states };
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e = cudaErrorInvalidValue;
-    if (sh.mode == 0) {
+    if (sh.mode == 2) {
+#define X(GG, WW, LL) if (sh.G == GG && sh.W == WW && sh.L == LL) e = launch_rx_t<GG, WW, LL, 2, 0>(sh, ce, lc, a, st);
+	MULTI_COMBOS(X)
+#undef X
+    } else if (sh.mode == 0) {
 	/* FSK_B200_FILL: 0 (default) cp.async fill, group-masked loop; 1 TMA bulk copies
 	 * (UBLKCP + mbarrier); 3 cp.async fill, warp-synchronous loop.  The two alternatives
 	 * pass the same tests and measured slower (profiles/README.md); they are built for the
@@ -1482,6 +1521,10 @@ extern "C" int fsk_b200_cuda_rx_batch(void *p, const fsk_b200_geom *g, const fsk
     } else {
 	e = launch_rx_t<32, 1, 1, 1, 0>(sh, ce, lc, a, st);
     }
+    snprintf(ce->last_kernel, sizeof(ce->last_kernel),
+	    "k_rx<G=%d,W=%d,L=%d,mode=%d(%s),fill=%d> threads=%d ring=%u smem=%zu blocks=%d", sh.G, sh.W, sh.L, sh.mode,
+	    sh.mode == 2 ? "shared-segment" : sh.mode == 0 ? "per-candidate" : "generic", sh.mode == 0 ? ce->fill : 0,
+	    sh.wpb * 32, sh.ring, sh.smem, sh.blocks);
     if (e != cudaSuccess) {
 	fsk_b200_set_error("rx_batch launch (G=%d W=%d L=%d mode=%d ring=%u smem=%zu): %s", sh.G, sh.W,
 		sh.L, sh.mode, sh.ring, sh.smem, cudaGetErrorString(e));

@@ -172,6 +172,30 @@ static inline T shfl_xor(unsigned mask, T v, int o)
     return r;
 }
 
+/* __shfl_sync(mask, v, srcLane, width): the source is lane (srcLane mod width) of the caller's
+ * width-wide segment of the warp */
+template <class T>
+static inline T shfl_idx(unsigned mask, T v, int src_lane, int width)
+{
+    static_assert(sizeof(T) <= 8, "shuffle width");
+    Block *b = blk;
+    uint64_t bits = 0;
+    memcpy(&bits, &v, sizeof(T));
+    b->xchg[b->cur] = bits;
+    rendezvous(mask);
+    const unsigned lane = b->cur & 31u, w = (unsigned)width;
+    const unsigned src = (b->cur & ~31u) + (lane & ~(w - 1u)) + ((unsigned)src_lane & (w - 1u));
+    T r = v;
+    if (src < b->bdim.x) {
+	if (!((mask >> (src & 31u)) & 1u))
+	    die("__shfl_sync: source lane is not in the mask");
+	bits = b->xchg[src];
+	memcpy(&r, &bits, sizeof(T));
+    }
+    rendezvous(mask);
+    return r;
+}
+
 static inline unsigned ballot(unsigned mask, int pred)
 {
     Block *b = blk;
@@ -260,6 +284,8 @@ static inline void __syncthreads() { emu::wait_on(emu::blk->all, emu::blk->bdim.
 static inline void __syncwarp(unsigned mask = 0xffffffffu) { emu::rendezvous(mask); }
 template <class T>
 static inline T __shfl_xor_sync(unsigned mask, T v, int o) { return emu::shfl_xor(mask, v, o); }
+template <class T>
+static inline T __shfl_sync(unsigned mask, T v, int src_lane, int width = 32) { return emu::shfl_idx(mask, v, src_lane, width); }
 static inline int __any_sync(unsigned mask, int pred) { return emu::ballot(mask, pred) != 0u; }
 static inline unsigned __ballot_sync(unsigned mask, int pred) { return emu::ballot(mask, pred); }
 static inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
