@@ -221,11 +221,30 @@ int fsk_b200_find_frame_batch(fsk_b200_engine *e, const float *samples,
 	const float *limit, const uint8_t *expect_sel,
 	fsk_b200_frame *frames, void *stream);
 
+/* The same search, additionally exporting what fsk_bit_analyze (src/fsk.c:117-174) saw in every bit
+ * window of the WINNING candidate: bit_mags[(s*n_bits + b)*2 + 0] = the larger of the two tone
+ * magnitudes (the bit's signal, :163/:167), [.. + 1] = the smaller (its noise), both scaled by
+ * 2/bit_nsamples as at :132; n_bits = the length of the expect string.  Meaningful for streams whose
+ * returned confidence is > 0.  This is the hook the per-bit parity gate uses (tests); it costs one more
+ * analysis of the winner per stream.  bit_mags: device memory, 8-byte aligned. */
+int fsk_b200_find_frame_batch_bits(fsk_b200_engine *e, const float *samples,
+	size_t nstreams, size_t stride, const uint32_t *offset, const uint32_t *nvalid,
+	const uint32_t *try_first, const uint32_t *try_max, const uint32_t *try_step,
+	const float *limit, const uint8_t *expect_sel,
+	fsk_b200_frame *frames, float *bit_mags, void *stream);
+
 /* Batched rx loop (src/minimodem.c:1137-1463) over whole streams resident in
  * HBM: stream s is samples[s*stride .. s*stride + nsamples[s]) (nsamples NULL =
- * all `stride_valid` long).  Frame records go to frames[s*max_frames ...]; a
- * stream that would overflow max_frames stops with done=0.  `states` (device,
+ * all `nsamples_all` long; -EINVAL if that exceeds `stride`, per-stream lengths are
+ * clamped to it).  Frame records go to frames[s*max_frames ...].  `states` (device,
  * one per stream) must be zeroed for a fresh stream; it is updated in place.
+ * Limits: a row holds at most 2^32 - 4 samples (lengths and positions inside a row are
+ * 32-bit; longer recordings are fed in pieces, see fsk_b200_stream_push), a call at most
+ * 2^31 - 1 streams.
+ * Output overflow: a stream that has written max_frames records stops there with done = 0
+ * and nframes == max_frames; its position and loop state are saved, so it CAN be continued,
+ * but only after the caller has consumed the records and set states[s].nframes back to 0
+ * (fsk_b200_max_frames() sizes the buffer so that this never happens for a row of nsamples).
  * Asynchronous on `stream`.  Returns 0 or a negative errno. */
 int fsk_b200_rx_batch(fsk_b200_engine *e, const float *samples, size_t nstreams,
 	size_t stride, const uint32_t *nsamples, uint32_t nsamples_all,

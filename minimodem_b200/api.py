@@ -97,7 +97,7 @@ EXPORTS = [
     "fsk_set_tones_by_bandshift",
     "fsk_b200_rx_config_for_mode", "fsk_b200_rx_params_derive", "fsk_b200_engine_new",
     "fsk_b200_engine_destroy", "fsk_b200_engine_params", "fsk_b200_engine_tune",
-    "fsk_b200_find_frame_batch", "fsk_b200_rx_batch", "fsk_b200_rx_batch_host",
+    "fsk_b200_find_frame_batch", "fsk_b200_find_frame_batch_bits", "fsk_b200_rx_batch", "fsk_b200_rx_batch_host",
     "fsk_b200_max_frames", "fsk_b200_frame_databits", "fsk_b200_tx_batch", "fsk_b200_sin_table",
     "fsk_b200_s16_to_f32", "fsk_b200_rx_batch_host_s16", "fsk_b200_decode_ascii_batch",
     "fsk_b200_decode_batch", "fsk_b200_decoder_for_mode", "fsk_b200_decode_max_bytes_per_frame",
@@ -164,6 +164,10 @@ def lib():
     L.fsk_b200_find_frame_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, u32p, u32p,
                                             u32p, u32p, u32p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.fsk_b200_find_frame_batch.restype = C.c_int
+    L.fsk_b200_find_frame_batch_bits.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, u32p, u32p,
+                                                 u32p, u32p, u32p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                 C.c_void_p]
+    L.fsk_b200_find_frame_batch_bits.restype = C.c_int
     L.fsk_b200_rx_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, u32p, C.c_uint32,
                                     C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
     L.fsk_b200_rx_batch.restype = C.c_int
@@ -363,15 +367,26 @@ class RxEngine:
         return max_frames(self.params, nsamples)
 
     def find_frame_batch(self, samples, nvalid, try_first, try_max, try_step, limit,
-                         offset=None, expect_sel=None, frames=None, stream=None):
+                         offset=None, expect_sel=None, frames=None, stream=None, bit_mags=False):
         """samples: [nstreams, stride] float32 CUDA tensor; the rest: per-stream CUDA tensors
         (uint32 as int32 storage, float32 limit, uint8 expect_sel).  Returns frames as a
-        [nstreams, 5] int32 CUDA tensor (view with frames_to_numpy)."""
+        [nstreams, 5] int32 CUDA tensor (view with frames_to_numpy); with bit_mags=True also a
+        [nstreams, n_bits, 2] float32 tensor of the winning candidate's per-bit (signal, noise)
+        magnitudes (fsk_b200_find_frame_batch_bits)."""
         torch = _torch()
         assert samples.is_cuda and samples.dtype == torch.float32 and samples.is_contiguous()
         nstreams, stride = samples.shape
         if frames is None:
             frames = torch.empty((nstreams, 5), dtype=torch.int32, device=samples.device)
+        if bit_mags:
+            mags = torch.zeros((nstreams, self.params.expect_n_bits, 2), dtype=torch.float32, device=samples.device)
+            rc = lib().fsk_b200_find_frame_batch_bits(self._e, _ptr(samples), nstreams, stride, _ptr(offset),
+                                                      _ptr(nvalid), _ptr(try_first), _ptr(try_max), _ptr(try_step),
+                                                      _ptr(limit), _ptr(expect_sel), _ptr(frames), _ptr(mags),
+                                                      _stream_handle(stream))
+            if rc:
+                _err("fsk_b200_find_frame_batch_bits", rc)
+            return frames, mags
         rc = lib().fsk_b200_find_frame_batch(self._e, _ptr(samples), nstreams, stride, _ptr(offset),
                                              _ptr(nvalid), _ptr(try_first), _ptr(try_max), _ptr(try_step),
                                              _ptr(limit), _ptr(expect_sel), _ptr(frames),

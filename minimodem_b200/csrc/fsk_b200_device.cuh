@@ -398,7 +398,8 @@ struct Found {
 template <int G, int W, int L, bool WS, bool CONSEC>
 __device__ __forceinline__ float frame_finish(float (&acc)[W][4], const float *const (&p)[W],
 	const unsigned own_mask, const unsigned exp_bits, const fsk_b200_geom &geo, const float4 *tw, int sel,
-	unsigned g, unsigned gmask_in, unsigned &bits_lo_out, unsigned &bits_hi_out, float &ampl_out)
+	unsigned g, unsigned gmask_in, unsigned &bits_lo_out, unsigned &bits_hi_out, float &ampl_out,
+	float2 *bit_mags = nullptr)
 {
     const unsigned gmask = WS ? 0xffffffffu : gmask_in;
     constexpr unsigned WPP = G / L;
@@ -497,6 +498,8 @@ __device__ __forceinline__ float frame_finish(float (&acc)[W][4], const float *c
 	    const float noise = one[k] ? mag_space : mag_mark;
 	    const unsigned e = (exp_bits >> (2u * (jsel + (sel ? (unsigned)W : 0u)))) & 3u;
 	    mismatch |= e != 2u && e != (one[k] ? 1u : 0u);	/* pass 1, :211 */
+	    if (bit_mags)		/* diagnostics: the (signal, noise) magnitudes of src/fsk.c:158-169, scaled as there */
+		bit_mags[w] = make_float2(sig[k] * geo.mag_scalar, noise * geo.mag_scalar);
 	    if (noise > eps_u)					/* :279 */
 		tn += noise;
 	    if (one[k]) {
@@ -583,7 +586,7 @@ template <int G, int W, int L, bool WS = false>
 __device__ __forceinline__ float frame_analyze_fast(const Ring rg, unsigned cand_off,
 	const fsk_b200_geom &geo, const LaneWin<W> &lw, int sel, unsigned tw_s,
 	unsigned g, unsigned gmask_in, unsigned &bits_lo_out, unsigned &bits_hi_out, float &ampl_out,
-	int avail, bool &pending)
+	int avail, bool &pending, float2 *bit_mags = nullptr)
 {
     /* WS ("warp-synchronous"): the caller guarantees that all 32 lanes are here together, so
      * shuffles and votes use the constant full mask (the shuffle distances stay inside a
@@ -630,7 +633,7 @@ __device__ __forceinline__ float frame_analyze_fast(const Ring rg, unsigned cand
     }
     corr_pass<SJ, W, W, L>(acc, p, tw, part, N);
     return frame_finish<G, W, L, WS, false>(acc, p, lw.own, lw.exp, geo, tw, sel, g, gmask_in, bits_lo_out,
-	    bits_hi_out, ampl_out);
+	    bits_hi_out, ampl_out, bit_mags);
 }
 
 /* The zig-zag search of src/fsk.c:477-502 run warp-synchronously: every lane of the warp
@@ -805,6 +808,7 @@ __device__ __forceinline__ Found find_frame_multi(const Ring rg, unsigned pos_of
     Found best = { 0.f, 0.f, 0u, 0u, 0u };
     unsigned best_order = 0;
 
+#pragma unroll 1
     for (unsigned b = 0; b < kind.nbatch; b++) {
 	const fsk_b200_mbatch &mb = kind.b[b];
 	const unsigned anchor_off = ring_wrap(pos_off + mb.anchor, R);
@@ -835,6 +839,7 @@ __device__ __forceinline__ Found find_frame_multi(const Ring rg, unsigned pos_of
 	}
 	corr_multi<W, L>(acc, p0, p1, p2, tw, part, mb.rho1, mb.rho2, N);
 
+#pragma unroll 1
 	for (unsigned i = 0; i < mb.ncand; i++) {
 	    const unsigned cs = mb.cseg[i];
 	    const int shift = mb.shift[i];

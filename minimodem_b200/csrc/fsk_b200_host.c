@@ -609,7 +609,26 @@ int fsk_b200_find_frame_batch(fsk_b200_engine *e, const float *samples, size_t n
 	return -EINVAL;
     }
     return fsk_b200_cuda_find_frame_batch(e->ce, &e->geom, samples, nstreams, stride, offset,
-	    nvalid, try_first, try_max, try_step, limit, expect_sel, frames, stream);
+	    nvalid, try_first, try_max, try_step, limit, expect_sel, frames, NULL, stream);
+}
+
+int fsk_b200_find_frame_batch_bits(fsk_b200_engine *e, const float *samples, size_t nstreams,
+	size_t stride, const uint32_t *offset, const uint32_t *nvalid,
+	const uint32_t *try_first, const uint32_t *try_max, const uint32_t *try_step,
+	const float *limit, const uint8_t *expect_sel, fsk_b200_frame *frames, float *bit_mags, void *stream)
+{
+    if (nstreams == 0)
+	return 0;
+    int rc = check_layout(samples, stride);
+    if (rc)
+	return rc;
+    if (!nvalid || !try_first || !try_max || !try_step || !limit || !frames || !bit_mags
+	    || ((uintptr_t)bit_mags & 7)) {
+	fsk_b200_set_error("find_frame_batch_bits: NULL or misaligned argument");
+	return -EINVAL;
+    }
+    return fsk_b200_cuda_find_frame_batch(e->ce, &e->geom, samples, nstreams, stride, offset,
+	    nvalid, try_first, try_max, try_step, limit, expect_sel, frames, bit_mags, stream);
 }
 
 int fsk_b200_rx_batch(fsk_b200_engine *e, const float *samples, size_t nstreams, size_t stride,

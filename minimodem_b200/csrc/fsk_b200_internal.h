@@ -89,7 +89,7 @@ int  fsk_b200_cuda_tune(void *ce, int lanes_per_stream, int warps_per_block, int
 int  fsk_b200_cuda_find_frame_batch(void *ce, const fsk_b200_geom *g, const float *samples,
 	size_t nstreams, size_t stride, const uint32_t *offset, const uint32_t *nvalid,
 	const uint32_t *try_first, const uint32_t *try_max, const uint32_t *try_step,
-	const float *limit, const uint8_t *expect_sel, fsk_b200_frame *frames, void *stream);
+	const float *limit, const uint8_t *expect_sel, fsk_b200_frame *frames, float *bit_mags, void *stream);
 int  fsk_b200_cuda_rx_batch(void *ce, const fsk_b200_geom *g, const fsk_b200_loopc *lc,
 	const float *samples, size_t nstreams, size_t stride, const uint32_t *nsamples,
 	uint32_t nsamples_all, fsk_b200_frame *frames, uint32_t max_frames,

@@ -110,6 +110,7 @@ struct FindArgs {
     const float *limit;
     const uint8_t *expect_sel;
     fsk_b200_frame *frames;
+    float2 *bit_mags;		/* optional diagnostics: [nstreams][n_bits] (signal, noise) of the winning candidate */
 };
 
 struct RxArgs {
@@ -168,10 +169,28 @@ k_find_frame(const __grid_constant__ fsk_b200_geom geo, const float4 *__restrict
 		ampl = f.amplitude;
 		start = f.start;
 		bits = ((unsigned long long)f.bits_hi << 32) | f.bits_lo;
+		if (a.bit_mags) {		/* analyse the winner once more, exporting its per-bit magnitudes */
+		    unsigned lo, hi;
+		    float am;
+		    bool nopend = false;
+		    __syncwarp(gmask);
+		    (void)frame_analyze_fast<G, W, L>(rg, ring_wrap((off & 3u) + f.start, rg.R), geo, lw, sel, tw_s,
+			    g, gmask, lo, hi, am, 0, nopend, a.bit_mags + (size_t)s * geo.n_bits);
+		}
 	    } else {
 		const GlobalSrc src = { x, n };
 		conf = find_frame<G, GlobalSrc>(src, off, geo, sel, sm.tw, sm.scr, g, gmask,
 			a.try_first[s], tmax, tstep, a.limit[s], bits, ampl, start);
+		if (a.bit_mags) {
+		    unsigned long long b2;
+		    float am;
+		    (void)frame_analyze<G, GlobalSrc>(src, off + start, geo, sel, sm.tw, sm.scr, g, gmask, b2, am);
+		    __syncwarp(gmask);
+		    /* the scratch holds (signal, +-noise) per bit unless pass 1 rejected the candidate midway */
+		    for (unsigned w = g; w < geo.n_bits; w += G)
+			a.bit_mags[(size_t)s * geo.n_bits + w] = make_float2(sm.scr[w].x, fabsf(sm.scr[w].y));
+		    __syncwarp(gmask);
+		}
 	    }
 	}
 	if (g == 0)
@@ -1222,7 +1241,7 @@ struct Shape {
 /* (G, W, L) combinations that are instantiated for the fast path: G lanes per
  * stream, L lanes per bit window, W windows per lane (W * G/L >= n_bits) */
 #ifdef FSK_EXPERIMENT		/* quick builds for tuning runs */
-#define FAST_COMBOS(X) X(8, 3, 2) X(8, 2, 1) X(4, 3, 1) X(16, 3, 4) X(8, 1, 1) X(8, 2, 2)
+#define FAST_COMBOS(X) X(8, 3, 2) X(8, 2, 1) X(4, 3, 1) X(16, 3, 4) X(8, 1, 1) X(8, 2, 2) X(8, 4, 4)
 #else
 #define FAST_COMBOS(X) \
     X(4, 1, 1) X(4, 2, 1) X(4, 3, 1) X(4, 4, 1) X(4, 2, 2) X(4, 4, 2) \
@@ -1414,7 +1433,7 @@ static cudaError_t launch_find_t(const Shape &sh, const CudaEngine *ce, const Fi
 extern "C" int fsk_b200_cuda_find_frame_batch(void *p, const fsk_b200_geom *g, const float *samples,
 	size_t nstreams, size_t stride, const uint32_t *offset, const uint32_t *nvalid,
 	const uint32_t *try_first, const uint32_t *try_max, const uint32_t *try_step,
-	const float *limit, const uint8_t *expect_sel, fsk_b200_frame *frames, void *stream)
+	const float *limit, const uint8_t *expect_sel, fsk_b200_frame *frames, float *bit_mags, void *stream)
 {
     CudaEngine *ce = (CudaEngine *)p;
     if (!ce->d_tw || ce->tw_n < g->bit_nsamples) {
@@ -1427,7 +1446,7 @@ extern "C" int fsk_b200_cuda_find_frame_batch(void *p, const fsk_b200_geom *g, c
     /* the ring is sized for the widest search of the rx loop: 1.5 bits + span */
     pick_shape(ce, g, g->span + 2u * g->bit_nsamples + 8u, 0, nstreams, &sh);
     const FindArgs a = { samples, (unsigned)nstreams, stride, offset, nvalid, try_first, try_max,
-	try_step, limit, expect_sel, frames };
+	try_step, limit, expect_sel, frames, reinterpret_cast<float2 *>(bit_mags) };
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e = cudaErrorInvalidValue;
     if (sh.mode == 0) {
@@ -1709,7 +1728,7 @@ extern "C" int fsk_b200_cuda_find_frame_one(void *p, const fsk_b200_geom *g, con
     CUDA_TRY(cudaMemcpy(ce->d_args, args, sizeof(args), cudaMemcpyHostToDevice));
     int rc = fsk_b200_cuda_find_frame_batch(ce, g, ce->d_one, 1, cap, ce->d_args + 0, ce->d_args + 1,
 	    ce->d_args + 2, ce->d_args + 3, ce->d_args + 4, (const float *)(ce->d_args + 5), NULL,
-	    ce->d_frame, NULL);
+	    ce->d_frame, NULL, NULL);
     if (rc)
 	return rc;
     CUDA_TRY(cudaMemcpy(out, ce->d_frame, sizeof(*out), cudaMemcpyDeviceToHost));

@@ -999,3 +999,153 @@ def test_live_receiver_prints_the_reference_output_however_the_stream_is_cut(nam
     assert int(lr.dropped.sum()) == 0
     for i in range(nstreams):
         assert bytes(text[i]) == bytes(g["stdout"]), i
+
+
+# --------------------------------------------------------------------------
+# per-bit parity gate (SURVEY.md 7 hard part 3): what fsk_bit_analyze saw in every
+# bit window of the winning candidate -- signal and noise magnitudes of src/fsk.c:158-169 --
+# against the oracle's: rel 1e-4 on the signal, abs 1e-4 * (mean signal) on the noise, and the
+# noise <= FLT_EPSILON class of :278-280 (what makes `confidence=inf`) exactly
+# --------------------------------------------------------------------------
+PERBIT_MODES = [("1200", {}), ("rtty", dict(sample_rate=8000)), ("300", {}), ("same", {}),
+                ("1200", dict(mark=1200, space=2400))]          # the last: orthogonal tones, the -P vectors' geometry
+
+
+@pytest.mark.parametrize("mode,kw", PERBIT_MODES, ids=["cfg2-1200", "cfg3-rtty8k", "cfg4-bell103", "cfg5-same", "purefreqs"])
+def test_per_bit_magnitudes_vs_oracle(mode, kw):
+    m = orc.Mode(mode, **kw)
+    d = m.derived()
+    eng, _ = engine_for((mode, kw))
+    rng = np.random.default_rng(7)
+    words = rng.integers(32 if m.n_data_bits >= 7 else 0, 127 if m.n_data_bits >= 7 else 1 << m.n_data_bits,
+                         40, dtype=np.uint32)
+    clean = orc.tx_words(m, words, 1.0, 4096, True)
+    spb = float(d.nsamples_per_bit)
+    plan = orc.Plan(m.sample_rate, m.mark_f, m.space_f, m.band_width)
+    nstreams = 192
+    tmc = int(np.float32(np.float32(spb) * np.float32(0.75) + np.float32(0.5))) + d.nsamples_overscan
+    wlen = pad4(tmc + d.expect_nsamples + int(spb) + 8)
+    buf = np.zeros((nstreams, wlen), np.float32)
+    first = d.nsamples_overscan
+    for s in range(nstreams):
+        sigma = (0.0, 0.0, 0.05, 0.3)[s % 4]
+        pos = int(rng.integers(0, clean.size - wlen))
+        buf[s] = (clean[pos:pos + wlen] + sigma * rng.standard_normal(wlen)).astype(np.float32)
+    t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(np.asarray(a).astype(dt))).to(dev())
+    full = lambda v, dt: t(np.full(nstreams, v), dt)
+    step = max(tmc // 8, 1)
+    frames, mags = eng.find_frame_batch(t(buf, np.float32), full(wlen, np.int32), full(first, np.int32),
+                                        full(tmc, np.int32), full(step, np.int32), full(np.inf, np.float32),
+                                        bit_mags=True)
+    torch.cuda.synchronize()
+    fr = mm.frames_to_numpy(frames)
+    mg = mags.cpu().numpy()
+    eps = np.float32(1.1920928955078125e-07)
+    n_checked = n_inf = 0
+    for s in range(nstreams):
+        if not fr[s]["confidence"] > 0:
+            continue
+        start = int(fr[s]["frame_start"])
+        spb_fsk = float(np.float32(d.expect_nsamples) / np.float32(d.expect_n_bits))     # src/fsk.c:465
+        c, bits, ampl, sig, noise, val = plan.frame_analyze(buf[s, start:].copy(), spb_fsk, d.expect_data)
+        got_bits = int(fr[s]["bits_lo"]) | (int(fr[s]["bits_hi"]) << 32)
+        assert got_bits == bits, (mode, s)
+        avg = float(np.mean(sig))
+        assert np.allclose(mg[s, :, 0], sig, rtol=1e-4, atol=0), (mode, s, mg[s, :, 0], sig)
+        assert np.allclose(mg[s, :, 1], noise, rtol=0, atol=1e-4 * avg), (mode, s, mg[s, :, 1], noise)
+        # the confidence=inf class: a noise magnitude at or below FLT_EPSILON is dropped from the sum (:279)
+        assert np.array_equal(mg[s, :, 1] <= eps, noise <= eps), (mode, s, mg[s, :, 1], noise)
+        n_inf += int((noise <= eps).any())
+        n_checked += 1
+    assert n_checked > nstreams // 4, n_checked
+    if kw.get("space") == 2400:
+        assert n_inf > 0            # the clean streams of this geometry do hit the class
+
+
+# --------------------------------------------------------------------------
+# every shipped rx kernel variant on hardware: the cp.async fill with the shared-segment search
+# (default where the mode allows it) and with the per-candidate search, the TMA bulk fill
+# (cp.async.bulk + mbarrier, FILL=1) and the warp-synchronous loop (FILL=3), each against the
+# oracle on the same streams
+# --------------------------------------------------------------------------
+@pytest.mark.parametrize("variant", ["multi", "per-candidate", "tma-bulk", "warp-sync"])
+@pytest.mark.parametrize("name", ["01-self-test-1200", "02-self-test-300", "small-rtty"])
+def test_rx_kernel_variants_agree_with_the_oracle(name, variant, monkeypatch):
+    env = {"multi": {}, "per-candidate": {"FSK_B200_MULTI": "0"},
+           "tma-bulk": {"FSK_B200_FILL": "1"}, "warp-sync": {"FSK_B200_FILL": "3"}}[variant]
+    import conftest
+    if variant == "tma-bulk" and conftest.EMU_DEVICE is not None:
+        pytest.skip("the host emulation does not model cp.async.bulk / mbarrier")
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)                # read when the engine is created
+    case = refcases.BY_NAME[name]
+    g = gu.load(case["name"])
+    _, rx = gu.modes(case)
+    a = gu.audio(case, g)
+    eng, _ = engine_for(case)
+    rng = np.random.default_rng(3)
+    streams = [np.concatenate([np.zeros(int(rng.integers(0, 97)), np.float32), a]) for _ in range(9)]
+    streams.append((a + 0.05 * rng.standard_normal(a.size)).astype(np.float32))
+    recs, st = rx_on_gpu(eng, streams)
+    kern = eng.last_kernel()
+    if variant == "multi":
+        assert "shared-segment" in kern, kern
+    elif variant == "per-candidate":
+        assert "per-candidate" in kern, kern
+    else:
+        assert "fill=%s" % env["FSK_B200_FILL"] in kern, kern
+    for s, x in enumerate(streams):
+        want = orc.rx_run(rx, x, literal=False)
+        compare_frames(as_oracle_frames(recs[s]), want["frames"], "%s %s stream %d" % (name, variant, s))
+
+
+# --------------------------------------------------------------------------
+# the BASELINE configurations at batch sizes of the bench's order (>= 16 384 streams each), generated
+# on the device, a 1 % sample of the streams compared with the oracle frame by frame
+# --------------------------------------------------------------------------
+@pytest.mark.parametrize("mode,kw,nstreams,nwords,sigma", [
+    ("1200", {}, 16384, 40, 0.0), ("1200", {}, 16384, 40, 0.35),
+    ("rtty", dict(sample_rate=8000), 16384, 12, 0.0),
+    ("300", {}, 16384, 12, 0.0), ("300", {}, 16384, 12, 0.25),
+    ("same", {}, 16384, 24, 0.0)],
+    ids=["cfg2", "cfg2-awgn", "cfg3-rtty8k", "cfg4-bell103", "cfg4-bell103-awgn", "cfg5-same"])
+def test_baseline_configs_large_batch_sample_vs_oracle(mode, kw, nstreams, nwords, sigma):
+    import conftest
+    if conftest.EMU_DEVICE is not None:
+        nstreams = 256                      # the host emulation is ~10^4 x slower
+    m = orc.Mode(mode, **kw)
+    d = m.derived()
+    eng, cfg = engine_for((mode, kw))
+    tcfg = mm.tx_config_from(cfg)
+    gen = torch.Generator(device="cpu").manual_seed(5)
+    mask = (1 << m.n_data_bits) - 1
+    lo, hi = (32, 127) if m.n_data_bits >= 7 else (0, 1 << m.n_data_bits)
+    words = (torch.randint(lo, hi, (nstreams, nwords), generator=gen, dtype=torch.int32) & mask)
+    max_lead = 0 if cfg.do_rx_sync else max(1, int(d.nsamples_per_bit))
+    lead = (torch.randint(0, max_lead, (nstreams,), generator=gen, dtype=torch.int32) if max_lead
+            else torch.zeros(nstreams, dtype=torch.int32))
+    n = int(orc.lib().orc_tx_nsamples(C.byref(m.tx_config(1.0, 4096, True)), nwords)) + max_lead + 64
+    x = mm.tx_batch(tcfg, words.to(dev()), n, lead_in=lead.to(dev()))
+    if sigma:
+        g2 = torch.Generator(device="cpu").manual_seed(6)
+        x = x + (sigma * torch.randn(x.shape, generator=g2, dtype=torch.float32)).to(dev())
+        x = x.contiguous()
+    frames, states = eng.rx_batch(x, nsamples=n)
+    torch.cuda.synchronize()
+    assert ("shared-segment" in eng.last_kernel()) == (mode != "same"), eng.last_kernel()
+    st = mm.states_to_numpy(states)
+    assert (st["done"] == 1).all()
+    rows = np.arange(0, nstreams, max(1, nstreams // max(8, nstreams // 100)))
+    fr = mm.frames_to_numpy(frames[torch.from_numpy(rows).to(dev())])
+    hx = x[torch.from_numpy(rows).to(dev())].cpu().numpy()
+    n_flip = 0
+    for i, s in enumerate(rows):
+        want = orc.rx_run(m, hx[i, :n].copy(), literal=False)
+        got = as_oracle_frames(fr[i, :st["nframes"][s]])
+        try:
+            compare_frames(got, want["frames"], "%s stream %d" % (mode, s))
+        except AssertionError:
+            assert sigma > 0, (mode, s)         # clean streams: exact
+            n_flip += 1
+            assert [orc.databits(m, f[0]) for f in got][:4] == [orc.databits(m, f[0]) for f in want["frames"]][:4]
+    assert n_flip <= max(1, len(rows) // 50), (n_flip, len(rows))
