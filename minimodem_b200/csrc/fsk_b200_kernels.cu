@@ -516,7 +516,7 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
 		    float amplitude2, confidence2;
 		    unsigned frame_start2;
 		    /* `carrier` is 1 by now, so the data string is searched (:1378) */
-		    if (MODE == 0) {
+		    if (MODE != 1) {
 			confidence2 = refined.confidence;	/* searched above */
 			amplitude2 = refined.amplitude;
 			frame_start2 = refined.start;
