@@ -193,7 +193,7 @@ typedef struct fsk_b200_stream_state {
      * src/minimodem.c:1265/:1373) by the fast rx kernel; 0 on the generic path */
     uint32_t	stat_candidates;
     uint32_t	stat_searches;
-    uint32_t	reserved;
+    uint32_t	reserved;	/* engine-private search hint (part of the resumable state; keep it with the rest) */
 } fsk_b200_stream_state;
 
 typedef struct fsk_b200_engine fsk_b200_engine;

@@ -582,9 +582,9 @@ __device__ __forceinline__ float frame_finish(float (&acc)[W][4], const float *c
  * to memory, and the frame statistics of src/fsk.c:271-336 are formed by
  * butterfly reductions over the group instead of a serial loop over the bits
  * (same terms, different but fixed summation order). */
-template <int G, int W, int L, bool WS = false>
+template <int G, int W, int L, bool WS = false, bool CONSEC = false, class LW = LaneWin<W> >
 __device__ __forceinline__ float frame_analyze_fast(const Ring rg, unsigned cand_off,
-	const fsk_b200_geom &geo, const LaneWin<W> &lw, int sel, unsigned tw_s,
+	const fsk_b200_geom &geo, const LW &lw, int sel, unsigned tw_s,
 	unsigned g, unsigned gmask_in, unsigned &bits_lo_out, unsigned &bits_hi_out, float &ampl_out,
 	int avail, bool &pending, float2 *bit_mags = nullptr)
 {
@@ -632,7 +632,7 @@ __device__ __forceinline__ float frame_analyze_fast(const Ring rg, unsigned cand
 	pending = false;
     }
     corr_pass<SJ, W, W, L>(acc, p, tw, part, N);
-    return frame_finish<G, W, L, WS, false>(acc, p, lw.own, lw.exp, geo, tw, sel, g, gmask_in, bits_lo_out,
+    return frame_finish<G, W, L, WS, CONSEC>(acc, p, lw.own, lw.exp, geo, tw, sel, g, gmask_in, bits_lo_out,
 	    bits_hi_out, ampl_out, bit_mags);
 }
 
@@ -734,6 +734,7 @@ struct LaneWinM {
     unsigned own;	/* bit j: this lane decides window j (one of the L lanes of the slot, round-robin) */
     unsigned exp;	/* 2 bits per (sel, j): expect value 0, 1 or 2 */
     unsigned wrapj;	/* the j whose slot is the wrap-around slot (period -1), W if it is not this lane's */
+    unsigned a_end;	/* unused (interface of LaneWin) */
 };
 
 template <int G, int W, int L>
@@ -745,6 +746,7 @@ __device__ __forceinline__ LaneWinM<W> lane_windows_multi(const fsk_b200_geom &g
     lw.own = 0;
     lw.exp = 0;
     lw.wrapj = W;
+    lw.a_end = 0;
 #pragma unroll
     for (int j = 0; j < W; j++) {
 	const unsigned m = slot * W + j;
@@ -794,19 +796,27 @@ __device__ __forceinline__ void rot_add(float &x, float &y, float a, float b, fl
     y += fmaf(c, b, s * a);
 }
 
-/* one search of the rx loop (src/fsk.c:449-538 as called at src/minimodem.c:1265 / :1373), all of
- * its candidates from shared segment sums */
+struct FoundN {
+    Found f;
+    unsigned ncand;		/* candidates analysed by this call */
+};
+
+/* One search of the rx loop (src/fsk.c:449-538 as called at src/minimodem.c:1265 / :1373), all of
+ * its candidates from shared segment sums.  `skip_first`: the candidate visited first has already
+ * been analysed by the caller (the single-candidate fast path of the steady state) and `seed` is
+ * the search's best-so-far after it.  A call, not inlined: the 36 segment accumulators then get
+ * their own register allocation and the rx loop around the call keeps the one it had. */
 template <int G, int W, int L>
-__device__ __forceinline__ Found find_frame_multi(const Ring rg, unsigned pos_off,
-	const fsk_b200_geom &geo, const LaneWinM<W> &lw, int sel, unsigned tw_s, unsigned g, unsigned gmask,
-	const fsk_b200_mkind &kind, float limit, bool pending, unsigned &ncand)
+__device__ __noinline__ FoundN find_frame_multi(const Ring rg, unsigned pos_off,
+	const fsk_b200_geom &geo, const LaneWinM<W> lw, int sel, unsigned tw_s, unsigned g, unsigned gmask,
+	const fsk_b200_mkind &kind, float limit, bool pending, const Found seed, unsigned skip_first)
 {
     const float *ring = static_cast<const float *>(__cvta_shared_to_generic(rg.ring_s));
     const float4 *tw = static_cast<const float4 *>(__cvta_shared_to_generic(tw_s));
     const unsigned N = geo.bit_nsamples, R = rg.R;
     const unsigned part = g % L;
-    Found best = { 0.f, 0.f, 0u, 0u, 0u };
-    unsigned best_order = 0;
+    Found best = seed;
+    unsigned best_order = 0, ncand = 0;
 
 #pragma unroll 1
     for (unsigned b = 0; b < kind.nbatch; b++) {
@@ -840,7 +850,7 @@ __device__ __forceinline__ Found find_frame_multi(const Ring rg, unsigned pos_of
 	corr_multi<W, L>(acc, p0, p1, p2, tw, part, mb.rho1, mb.rho2, N);
 
 #pragma unroll 1
-	for (unsigned i = 0; i < mb.ncand; i++) {
+	for (unsigned i = (b == 0u ? skip_first : 0u); i < mb.ncand; i++) {
 	    const unsigned cs = mb.cseg[i];
 	    const int shift = mb.shift[i];
 	    const unsigned t = mb.t[i];
@@ -921,11 +931,11 @@ __device__ __forceinline__ Found find_frame_multi(const Ring rg, unsigned pos_of
 		best = Found{ c, a, t, lo, hi };
 		best_order = order;
 		if (c >= limit && kind.nbatch == 1u)
-		    return best;			/* first to reach the limit wins (:499) */
+		    return FoundN{ best, ncand };	/* first to reach the limit wins (:499) */
 	    }
 	}
     }
-    return best;
+    return FoundN{ best, ncand };
 }
 /* ------------------------------------------------------------------------ */
 /* asynchronous ring fill: HBM -> shared memory, 16 bytes per cp.async,     */

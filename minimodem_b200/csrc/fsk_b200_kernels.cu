@@ -254,6 +254,7 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
 	unsigned nframes_decoded = st.nframes_decoded;
 	unsigned done = 0;
 	unsigned ncand = 0, nsearch = 0;	/* statistics: candidates analysed, searches run */
+	bool mhint = st.reserved != 0u;		/* MODE 2: the latest coarse search needed more than its first candidate */
 
 	/* ring bookkeeping (MODE 0): ring offset of `pos`, and the absolute index up to
 	 * which the ring content has been REQUESTED (copies issued or zeros stored) */
@@ -419,12 +420,43 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
 		int which = sel;
 		for (int pass = 0;; pass++) {
 		    nsearch++;
-		    /* :1265, :1378.  MODE 2: all candidates of the search from shared segment sums; which plan:
-		     * the window is the one chosen at the top of the iteration (carrier then), coarse or fine */
-		    const Found f = MODE == 2
-			? find_frame_multi<G, W, L>(rg, pos_off, geo, lwm, which, tw_s, g, gmask,
-				mp.kind[(carrier ? 1 : 0) + (pass ? 2 : 0)], limit, pending, ncand)
-			: find_frame_fast_body<G, W, L>(rg, pos_off, geo, lw, which, tw_s, g,
+		    Found f;
+		    if (MODE == 2) {
+			/* :1265, :1378 from shared segment sums.  Which plan: the window is the one chosen at the
+			 * top of the iteration (carrier then), coarse or fine.  A coarse search in the steady
+			 * state ends at its first candidate (:499), and one candidate alone is cheapest analysed
+			 * by itself: that is tried first unless the previous coarse search of this stream needed
+			 * more than one (mhint); the fine search visits all of its candidates anyway. */
+			const fsk_b200_mkind &kind = mp.kind[(carrier ? 1 : 0) + (pass ? 2 : 0)];
+			Found seed = { 0.f, 0.f, 0u, 0u, 0u };
+			unsigned skip = 0;
+			bool decided = false;
+			if (pass == 0 && !mhint) {
+			    unsigned lo, hi;
+			    float am;
+			    const float c = frame_analyze_fast<G, W, L, false, true, LaneWinM<W> >(rg,
+				    ring_wrap(pos_off + try_first, R), geo, lwm, which, tw_s, g, gmask, lo, hi, am,
+				    ready - (int)try_first, pending);
+			    ncand++;
+			    if (0.f < c) {					/* src/fsk.c:492 */
+				seed = Found{ c, am, try_first, lo, hi };
+				decided = c >= limit;			/* :499 */
+			    }
+			    skip = 1;
+			    mhint = !decided;
+			}
+			if (decided)
+			    f = seed;
+			else {
+			    const FoundN r = find_frame_multi<G, W, L>(rg, pos_off, geo, lwm, which, tw_s, g, gmask,
+				    kind, limit, pending, seed, skip);
+			    f = r.f;
+			    ncand += r.ncand;
+			    if (pass == 0 && !skip)
+				mhint = r.ncand > 1u;
+			}
+		    } else
+			f = find_frame_fast_body<G, W, L>(rg, pos_off, geo, lw, which, tw_s, g,
 				gmask, try_first, try_max, step, limit, ready, pending, ncand);
 		    if (pass) {
 			refined = f;
@@ -576,6 +608,7 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
 	    st.done = done;
 	    st.stat_candidates += ncand;
 	    st.stat_searches += nsearch;
+	    st.reserved = mhint ? 1u : 0u;
 	    a.states[s] = st;
 	}
 	__syncwarp(gmask);
