@@ -807,7 +807,7 @@ struct FoundN {
  * the search's best-so-far after it.  A call, not inlined: the 36 segment accumulators then get
  * their own register allocation and the rx loop around the call keeps the one it had. */
 template <int G, int W, int L>
-__device__ __noinline__ FoundN find_frame_multi(const Ring rg, unsigned pos_off,
+__device__ __forceinline__ FoundN find_frame_multi(const Ring rg, unsigned pos_off,
 	const fsk_b200_geom &geo, const LaneWinM<W> lw, int sel, unsigned tw_s, unsigned g, unsigned gmask,
 	const fsk_b200_mkind &kind, float limit, bool pending, const Found seed, unsigned skip_first)
 {
