@@ -476,7 +476,9 @@ __device__ __forceinline__ float frame_finish(float (&acc)[W][4], const float *c
 	if (own[k]) {
 	    float mag_mark = fast_sqrt(a0 * a0 + a1 * a1);
 	    float mag_space = fast_sqrt(a2 * a2 + a3 * a3);
-	    if (fminf(mag_mark, mag_space) < eps_u + 2e-6f * fmaxf(mag_mark, mag_space)) {
+	    const float mag_hi = fmaxf(mag_mark, mag_space);
+	    /* (a window whose fp32 sums are exactly zero -- silence -- stays zero in fp64 too) */
+	    if (mag_hi != 0.f && fminf(mag_mark, mag_space) < eps_u + 2e-6f * mag_hi) {
 		/* too close to the :279 threshold for fp32 sums (see needs_resum): fp64 re-sum */
 		double drm = 0., dim = 0., drs = 0., dis = 0.;
 #pragma unroll 1
@@ -735,6 +737,9 @@ struct LaneWinM {
     unsigned exp;	/* 2 bits per (sel, j): expect value 0, 1 or 2 */
     unsigned wrapj;	/* the j whose slot is the wrap-around slot (period -1), W if it is not this lane's */
     unsigned a_end;	/* unused (interface of LaneWin) */
+    unsigned rot0;	/* this slot starts its walk over a period at sample rot0 (a multiple of L) and wraps:
+			 * periods are a multiple of the bank count apart in slow modes, so slots walking in
+			 * step would hit the same shared-memory banks */
 };
 
 template <int G, int W, int L>
@@ -759,17 +764,27 @@ __device__ __forceinline__ LaneWinM<W> lane_windows_multi(const fsk_b200_geom &g
 	if (m == SLOTS - 1u)
 	    lw.wrapj = j;
     }
+    {
+	/* bank of this slot's first sample relative to slot 0's, and where it should be: the G/L slots
+	 * of a group spread evenly over the 32 banks (each covers L consecutive ones) */
+	constexpr unsigned SPG = (unsigned)(G / L);
+	const unsigned have = (geo.bit_nsamples * (unsigned)W * slot) & 31u;
+	const unsigned want = (slot * (32u / SPG)) & 31u;
+	unsigned r = (want - have) & 31u;
+	r -= r % (unsigned)L;
+	lw.rot0 = r < geo.bit_nsamples ? r : 0u;
+    }
     return lw;
 }
 
 /* segment sums of this lane's W periods: one pass over the period, the accumulator set switching
- * at rho1 and rho2 (the loop variable simply runs on, so every lane keeps its n = part mod L) */
+ * at rho1 and rho2 (the loop variable simply runs on, so every lane keeps its n = part mod L).
+ * The walk starts at sample rot0 of the period and wraps (two halves: [rot0, N) then [0, rot0)). */
 template <int W, int L>
 __device__ __forceinline__ void corr_multi(float (&acc)[W][3][4], const float *const (&p0)[W],
 	const float *const (&p1)[W], const float *const (&p2)[W], const float4 *tw, unsigned part,
-	unsigned rho1, unsigned rho2, unsigned N)
+	unsigned rho1, unsigned rho2, unsigned N, unsigned rot0)
 {
-    unsigned n = part;
 #define FSK_SEG_LOOP(C, PTR, END) \
     _Pragma("unroll 4") \
     for (; n < (END); n += L) { \
@@ -783,9 +798,16 @@ __device__ __forceinline__ void corr_multi(float (&acc)[W][3][4], const float *c
 	    acc[j][C][3] = fmaf(x, c.w, acc[j][C][3]); \
 	} \
     }
-    FSK_SEG_LOOP(0, p0, rho1)
-    FSK_SEG_LOOP(1, p1, rho2)
-    FSK_SEG_LOOP(2, p2, N)
+#pragma unroll 1
+    for (int half = 0; half < 2; half++) {
+	const unsigned lo = half ? 0u : rot0, hi = half ? rot0 : N;	/* rot0 is a multiple of L */
+	unsigned n = lo + part;
+	const unsigned e0 = min(rho1, hi), e1 = min(rho2, hi);
+	/* n only grows: a segment that ends at or before n is skipped by its loop condition */
+	FSK_SEG_LOOP(0, p0, e0)
+	FSK_SEG_LOOP(1, p1, e1)
+	FSK_SEG_LOOP(2, p2, hi)
+    }
 #undef FSK_SEG_LOOP
 }
 
@@ -847,7 +869,7 @@ __device__ __forceinline__ FoundN find_frame_multi(const Ring rg, unsigned pos_o
 	    __syncwarp(gmask);
 	    pending = false;
 	}
-	corr_multi<W, L>(acc, p0, p1, p2, tw, part, mb.rho1, mb.rho2, N);
+	corr_multi<W, L>(acc, p0, p1, p2, tw, part, mb.rho1, mb.rho2, N, lw.rot0);
 
 #pragma unroll 1
 	for (unsigned i = (b == 0u ? skip_first : 0u); i < mb.ncand; i++) {

@@ -66,6 +66,7 @@ typedef struct fsk_b200_mkind {
  * the carrier still uses the no-carrier window (src/minimodem.c:1236-1263 are evaluated before :1357) */
 typedef struct fsk_b200_mplan {
     fsk_b200_mkind kind[4];
+    uint32_t	always;		/* 1: every coarse search goes through the shared segments (no single-candidate fast path) */
 } fsk_b200_mplan;
 /* 0 and the plan if every search kind of this mode can run on `slots` period slots, else -1 */
 int fsk_b200_mplan_build(const fsk_b200_geom *g, const struct fsk_b200_loopc *lc, unsigned int slots,

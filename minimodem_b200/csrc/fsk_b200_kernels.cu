@@ -220,7 +220,7 @@ k_find_frame(const __grid_constant__ fsk_b200_geom geo, const float4 *__restrict
 #define FSK_MAXTHREADS 128
 #endif
 template <int G, int W, int L, int MODE, int FILL>
-__global__ void __launch_bounds__(FSK_MAXTHREADS, FSK_MINBLOCKS)
+__global__ void __launch_bounds__(FSK_MAXTHREADS, (MODE == 2 && G >= 16) ? 3 : FSK_MINBLOCKS)
 k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200_loopc lc,
 	const float4 *__restrict__ tw_global, unsigned tw_in_smem, unsigned ring_floats,
 	unsigned lookahead, const __grid_constant__ RxArgs a, const __grid_constant__ fsk_b200_mplan mp)
@@ -431,7 +431,7 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
 			Found seed = { 0.f, 0.f, 0u, 0u, 0u };
 			unsigned skip = 0;
 			bool decided = false;
-			if (pass == 0 && !mhint) {
+			if (pass == 0 && !mhint && !mp.always) {
 			    unsigned lo, hi;
 			    float am;
 			    const float c = frame_analyze_fast<G, W, L, false, true, LaneWinM<W> >(rg,
@@ -1140,7 +1140,11 @@ extern "C" void *fsk_b200_cuda_engine_new(void)
     if ((e = getenv("FSK_B200_SPLIT"))) ce->split = atoi(e);
     ce->fill = 0;		/* see the dispatch in fsk_b200_cuda_rx_batch */
     if ((e = getenv("FSK_B200_FILL"))) ce->fill = atoi(e);
-    ce->multi = 1;
+    /* shared-segment search: -1 (default) = where it pays: modes with long bit periods, every coarse
+     * search through the shared segments (measured: Bell103 300 baud +40 %; at 40-sample periods the
+     * per-candidate kernel is faster, profiles/README.md); 0 never; 1 everywhere it fits, with the
+     * single-candidate fast path; 2 everywhere it fits, always */
+    ce->multi = -1;
     if ((e = getenv("FSK_B200_MULTI"))) ce->multi = atoi(e);
     /* 256 MiB of samples ON THE WIRE per slab, two slabs in flight: the float path runs at the PCIe
      * rate with that (54 GB/s).  The int16 path, measured with slabs of the same stream count (128 MiB
@@ -1284,6 +1288,9 @@ struct Shape {
     X(32, 1, 1) X(32, 2, 1) X(32, 1, 2) X(32, 2, 2) X(32, 3, 2) X(32, 4, 2) X(32, 1, 4) X(32, 2, 4) X(32, 3, 4) X(32, 4, 4)
 #endif
 
+#ifndef FSK_MULTI_MIN_N
+#define FSK_MULTI_MIN_N 96u	/* shortest bit period (samples) for which mode 2 is the default */
+#endif
 /* (G, W, L) of the shared-segment rx kernel (mode 2): W * G/L period slots >= n_bits + 1 */
 #define MULTI_COMBOS(X) \
     X(8, 2, 2) X(8, 3, 2) X(8, 4, 2) X(16, 2, 2) X(16, 3, 2) X(16, 4, 2) X(16, 2, 4) X(16, 3, 4) X(16, 4, 4) \
@@ -1418,13 +1425,14 @@ static int pick_shape(const CudaEngine *ce, const fsk_b200_geom *g, unsigned nee
 	}
     }
     sh->mode = fast ? 0 : 1;
-    if (fast && lc && ce->multi && ce->fill == 0) {
+    if (fast && lc && ce->multi && ce->fill == 0 && (ce->multi > 0 || g->bit_nsamples >= FSK_MULTI_MIN_N)) {
 	/* the rx loop's searches from shared segment sums, if this mode's windows tile and all of its
 	 * searches fit the period slots of a (W, L) split of this group size */
 	int W2 = 0, L2 = 0;
 	if (split_for_multi(G, g->n_bits + 1u, &W2, &L2) && g->bit_nsamples <= FAST_MAX_N * (unsigned)L2
 		&& fsk_b200_mplan_build(g, lc, (unsigned)(W2 * (G / L2)), &sh->mplan) == 0) {
 	    sh->mode = 2;
+	    sh->mplan.always = ce->multi >= 2 || ce->multi < 0;
 	    W = W2;
 	    L = L2;
 	}

@@ -1068,10 +1068,10 @@ def test_per_bit_magnitudes_vs_oracle(mode, kw):
 # (cp.async.bulk + mbarrier, FILL=1) and the warp-synchronous loop (FILL=3), each against the
 # oracle on the same streams
 # --------------------------------------------------------------------------
-@pytest.mark.parametrize("variant", ["multi", "per-candidate", "tma-bulk", "warp-sync"])
+@pytest.mark.parametrize("variant", ["multi", "multi-hybrid", "per-candidate", "tma-bulk", "warp-sync"])
 @pytest.mark.parametrize("name", ["01-self-test-1200", "02-self-test-300", "small-rtty"])
 def test_rx_kernel_variants_agree_with_the_oracle(name, variant, monkeypatch):
-    env = {"multi": {}, "per-candidate": {"FSK_B200_MULTI": "0"},
+    env = {"multi": {"FSK_B200_MULTI": "2"}, "multi-hybrid": {"FSK_B200_MULTI": "1"}, "per-candidate": {"FSK_B200_MULTI": "0"},
            "tma-bulk": {"FSK_B200_FILL": "1"}, "warp-sync": {"FSK_B200_FILL": "3"}}[variant]
     import conftest
     if variant == "tma-bulk" and conftest.EMU_DEVICE is not None:
@@ -1088,7 +1088,7 @@ def test_rx_kernel_variants_agree_with_the_oracle(name, variant, monkeypatch):
     streams.append((a + 0.05 * rng.standard_normal(a.size)).astype(np.float32))
     recs, st = rx_on_gpu(eng, streams)
     kern = eng.last_kernel()
-    if variant == "multi":
+    if variant.startswith("multi"):
         assert "shared-segment" in kern, kern
     elif variant == "per-candidate":
         assert "per-candidate" in kern, kern
@@ -1132,7 +1132,8 @@ def test_baseline_configs_large_batch_sample_vs_oracle(mode, kw, nstreams, nword
         x = x.contiguous()
     frames, states = eng.rx_batch(x, nsamples=n)
     torch.cuda.synchronize()
-    assert ("shared-segment" in eng.last_kernel()) == (mode != "same"), eng.last_kernel()
+    # the default policy: shared-segment search where the bit period is long and the windows tile
+    assert ("shared-segment" in eng.last_kernel()) == (mode in ("rtty", "300")), eng.last_kernel()
     st = mm.states_to_numpy(states)
     assert (st["done"] == 1).all()
     rows = np.arange(0, nstreams, max(1, nstreams // max(8, nstreams // 100)))
