@@ -765,13 +765,25 @@ __device__ __forceinline__ LaneWinM<W> lane_windows_multi(const fsk_b200_geom &g
 	    lw.wrapj = j;
     }
     {
-	/* bank of this slot's first sample relative to slot 0's, and where it should be: the G/L slots
-	 * of a group spread evenly over the 32 banks (each covers L consecutive ones) */
+	/* Bank of this slot's first sample relative to slot 0's: slot * (W * N mod 32).  If two slots of
+	 * the group come closer than L banks (each slot's L lanes read L neighbouring samples), the slots
+	 * start their walks L samples apart instead: sample loads are then conflict-free inside the
+	 * group and the twiddle rows of the slots fall into two bank classes (optimal for G/L * L rows
+	 * of 16 bytes).  Where the periods already spread the slots (1200 baud: 24 banks apart) nothing
+	 * rotates and all slots share their twiddle loads. */
 	constexpr unsigned SPG = (unsigned)(G / L);
-	const unsigned have = (geo.bit_nsamples * (unsigned)W * slot) & 31u;
-	const unsigned want = (slot * (32u / SPG)) & 31u;
-	unsigned r = (want - have) & 31u;
-	r -= r % (unsigned)L;
+	const unsigned stride = (geo.bit_nsamples * (unsigned)W) & 31u;
+	bool collide = false;
+	for (unsigned a = 0; a < SPG; a++)
+	    for (unsigned b = a + 1; b < SPG; b++) {
+		const unsigned d = ((b - a) * stride) & 31u;
+		collide |= d < (unsigned)L || 32u - d < (unsigned)L;
+	    }
+	unsigned r = 0;
+	if (collide) {
+	    r = (slot * (unsigned)L - slot * stride) & 31u;
+	    r -= r % (unsigned)L;
+	}
 	lw.rot0 = r < geo.bit_nsamples ? r : 0u;
     }
     return lw;
