@@ -737,9 +737,9 @@ struct LaneWinM {
     unsigned exp;	/* 2 bits per (sel, j): expect value 0, 1 or 2 */
     unsigned wrapj;	/* the j whose slot is the wrap-around slot (period -1), W if it is not this lane's */
     unsigned a_end;	/* unused (interface of LaneWin) */
-    unsigned rot0;	/* this slot starts its walk over a period at sample rot0 (a multiple of L) and wraps:
-			 * periods are a multiple of the bank count apart in slow modes, so slots walking in
-			 * step would hit the same shared-memory banks */
+    unsigned rot0;	/* this slot starts its walk over every segment rot0 iterations in, and wraps: periods are
+			 * a multiple of the bank count apart in slow modes, so slots walking in step would
+			 * hit the same shared-memory banks (0: the periods spread the slots by themselves) */
 };
 
 template <int G, int W, int L>
@@ -779,48 +779,68 @@ __device__ __forceinline__ LaneWinM<W> lane_windows_multi(const fsk_b200_geom &g
 		const unsigned d = ((b - a) * stride) & 31u;
 		collide |= d < (unsigned)L || 32u - d < (unsigned)L;
 	    }
-	unsigned r = 0;
-	if (collide) {
-	    r = (slot * (unsigned)L - slot * stride) & 31u;
-	    r -= r % (unsigned)L;
-	}
-	lw.rot0 = r < geo.bit_nsamples ? r : 0u;
+	/* iterations: slot s walks s * L samples (banks) ahead; bit 31 = the group rotates at all (uniform) */
+	lw.rot0 = collide ? (slot | 0x80000000u) : 0u;
     }
     return lw;
 }
 
-/* segment sums of this lane's W periods: one pass over the period, the accumulator set switching
- * at rho1 and rho2 (the loop variable simply runs on, so every lane keeps its n = part mod L).
- * The walk starts at sample rot0 of the period and wraps (two halves: [rot0, N) then [0, rot0)). */
+/* segment sums of this lane's W periods: one walk over the period, the accumulator set switching
+ * at rho1 and rho2.  Inside every segment the walk of a slot that would collide with the other
+ * slots' shared-memory banks (LaneWinM.rot0 > 0) starts rot0 iterations in and wraps: the slots
+ * then stay rot0 iterations -- L*rot0 banks -- apart for the length of the segment.  (A rotation
+ * of the whole period does not survive: the slots re-converge at every segment boundary.)  The
+ * loops are unrolled by hand, remainder LAST: the compiler's remainder-first unrolling re-aligns
+ * slots whose trip counts differ. */
+template <int C, int W, int L>
+__device__ __forceinline__ void seg_walk(float (&acc)[W][3][4], const float *const (&ptr)[W], const float4 *tw,
+	unsigned n, const unsigned end)
+{
+#define FSK_SEG_STEP(NN) { \
+	const float4 c = tw[NN]; \
+	_Pragma("unroll") \
+	for (int j = 0; j < W; j++) { \
+	    const float x = ptr[j][NN]; \
+	    acc[j][C][0] = fmaf(x, c.x, acc[j][C][0]); \
+	    acc[j][C][1] = fmaf(x, c.y, acc[j][C][1]); \
+	    acc[j][C][2] = fmaf(x, c.z, acc[j][C][2]); \
+	    acc[j][C][3] = fmaf(x, c.w, acc[j][C][3]); \
+	} }
+#pragma unroll 1
+    for (; n + 3u * L < end; n += 4u * L) {
+	FSK_SEG_STEP(n)
+	FSK_SEG_STEP(n + L)
+	FSK_SEG_STEP(n + 2u * L)
+	FSK_SEG_STEP(n + 3u * L)
+    }
+#pragma unroll 1
+    for (; n < end; n += L)
+	FSK_SEG_STEP(n)
+#undef FSK_SEG_STEP
+}
+
 template <int W, int L>
 __device__ __forceinline__ void corr_multi(float (&acc)[W][3][4], const float *const (&p0)[W],
 	const float *const (&p1)[W], const float *const (&p2)[W], const float4 *tw, unsigned part,
 	unsigned rho1, unsigned rho2, unsigned N, unsigned rot0)
 {
-#define FSK_SEG_LOOP(C, PTR, END) \
-    _Pragma("unroll 4") \
-    for (; n < (END); n += L) { \
-	const float4 c = tw[n]; \
-	_Pragma("unroll") \
-	for (int j = 0; j < W; j++) { \
-	    const float x = PTR[j][n]; \
-	    acc[j][C][0] = fmaf(x, c.x, acc[j][C][0]); \
-	    acc[j][C][1] = fmaf(x, c.y, acc[j][C][1]); \
-	    acc[j][C][2] = fmaf(x, c.z, acc[j][C][2]); \
-	    acc[j][C][3] = fmaf(x, c.w, acc[j][C][3]); \
-	} \
+    /* first sample of this lane (n = part mod L) at or after a segment start */
+    auto first_in = [&](unsigned a) { return a + ((part + (unsigned)L - a % (unsigned)L) % (unsigned)L); };
+    const unsigned f0 = part, f1 = first_in(rho1), f2 = first_in(rho2);
+    if (rot0 == 0u) {			/* the same for every lane of the group */
+	seg_walk<0, W, L>(acc, p0, tw, f0, rho1);
+	seg_walk<1, W, L>(acc, p1, tw, f1, rho2);
+	seg_walk<2, W, L>(acc, p2, tw, f2, N);
+    } else {
+	const unsigned r = (rot0 & 0x7fffffffu) * (unsigned)L;
+	const unsigned m0 = min(f0 + r, rho1), m1 = min(f1 + r, rho2), m2 = min(f2 + r, N);
+	seg_walk<0, W, L>(acc, p0, tw, m0 >= rho1 ? rho1 : f0 + r, rho1);	/* from rot0 iterations in ... */
+	seg_walk<0, W, L>(acc, p0, tw, f0, m0 >= rho1 ? rho1 : f0 + r);	/* ... and the ones skipped */
+	seg_walk<1, W, L>(acc, p1, tw, m1 >= rho2 ? rho2 : f1 + r, rho2);
+	seg_walk<1, W, L>(acc, p1, tw, f1, m1 >= rho2 ? rho2 : f1 + r);
+	seg_walk<2, W, L>(acc, p2, tw, m2 >= N ? N : f2 + r, N);
+	seg_walk<2, W, L>(acc, p2, tw, f2, m2 >= N ? N : f2 + r);
     }
-#pragma unroll 1
-    for (int half = 0; half < 2; half++) {
-	const unsigned lo = half ? 0u : rot0, hi = half ? rot0 : N;	/* rot0 is a multiple of L */
-	unsigned n = lo + part;
-	const unsigned e0 = min(rho1, hi), e1 = min(rho2, hi);
-	/* n only grows: a segment that ends at or before n is skipped by its loop condition */
-	FSK_SEG_LOOP(0, p0, e0)
-	FSK_SEG_LOOP(1, p1, e1)
-	FSK_SEG_LOOP(2, p2, hi)
-    }
-#undef FSK_SEG_LOOP
 }
 
 /* (a + ib) * (c + is) added to (x + iy) */
