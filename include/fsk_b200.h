@@ -301,6 +301,18 @@ int fsk_b200_detect_carrier_batch(int fftsize, const float *samples, size_t nstr
  * half the bytes cross PCIe, the widening happens on the device. */
 int fsk_b200_s16_to_f32(const int16_t *src, float *dst, size_t nstreams, size_t stride, void *stream);
 
+/* fsk_b200_rx_batch over int16 PCM rows resident in HBM: the samples stay 2 bytes wide in device
+ * memory and are widened (short / 32768, exact) inside the rx kernel's shared-memory ring fill, so
+ * a sample costs 2 bytes of HBM traffic instead of the 2 + 4 + 4 of a separate widening pass.  Same
+ * records, bit for bit, as fsk_b200_rx_batch on the widened floats.  samples: device memory, 16-byte
+ * aligned; stride: a multiple of 8 samples.  -ENOTSUP when the mode's launch shape has no int16
+ * build (unusual framings; widen with fsk_b200_s16_to_f32 then).  fsk_b200_rx_batch_host_s16 uses
+ * this path whenever it can. */
+int fsk_b200_rx_batch_s16(fsk_b200_engine *e, const int16_t *samples, size_t nstreams,
+	size_t stride, const uint32_t *nsamples, uint32_t nsamples_all,
+	fsk_b200_frame *frames, uint32_t max_frames,
+	fsk_b200_stream_state *states, void *stream);
+
 /* N2, the file side: where the samples of a RIFF/WAVE image are (the container the reference's
  * tests and its default `--file` output use; the reference itself goes through libsndfile,
  * src/simpleaudio-sndfile.c:88-160).  Mono PCM16 (format 1) and IEEE float32 (format 3) only, which

@@ -97,7 +97,7 @@ EXPORTS = [
     "fsk_set_tones_by_bandshift",
     "fsk_b200_rx_config_for_mode", "fsk_b200_rx_params_derive", "fsk_b200_engine_new",
     "fsk_b200_engine_destroy", "fsk_b200_engine_params", "fsk_b200_engine_tune",
-    "fsk_b200_find_frame_batch", "fsk_b200_find_frame_batch_bits", "fsk_b200_rx_batch", "fsk_b200_rx_batch_host",
+    "fsk_b200_find_frame_batch", "fsk_b200_find_frame_batch_bits", "fsk_b200_rx_batch", "fsk_b200_rx_batch_s16", "fsk_b200_rx_batch_host",
     "fsk_b200_max_frames", "fsk_b200_frame_databits", "fsk_b200_tx_batch", "fsk_b200_sin_table",
     "fsk_b200_s16_to_f32", "fsk_b200_rx_batch_host_s16", "fsk_b200_decode_ascii_batch",
     "fsk_b200_decode_batch", "fsk_b200_decoder_for_mode", "fsk_b200_decode_max_bytes_per_frame",
@@ -171,6 +171,8 @@ def lib():
     L.fsk_b200_rx_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, u32p, C.c_uint32,
                                     C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
     L.fsk_b200_rx_batch.restype = C.c_int
+    L.fsk_b200_rx_batch_s16.argtypes = L.fsk_b200_rx_batch.argtypes
+    L.fsk_b200_rx_batch_s16.restype = C.c_int
     L.fsk_b200_rx_batch_host.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_uint32,
                                          C.c_void_p, C.c_uint32, C.c_void_p]
     L.fsk_b200_rx_batch_host.restype = C.c_int
@@ -400,7 +402,7 @@ class RxEngine:
         """The rx loop over every row of `samples` ([nstreams, stride] float32 CUDA tensor).
         Returns (frames [nstreams, max_frames, 5] int32, states [nstreams, STATE_WORDS] int32)."""
         torch = _torch()
-        assert samples.is_cuda and samples.dtype == torch.float32 and samples.is_contiguous()
+        assert samples.is_cuda and samples.dtype in (torch.float32, torch.int16) and samples.is_contiguous()
         nstreams, stride = samples.shape
         n_all = int(nsamples if nsamples is not None else stride)
         if max_frames is None:
@@ -409,8 +411,10 @@ class RxEngine:
             frames = torch.empty((nstreams, max_frames, 5), dtype=torch.int32, device=samples.device)
         if states is None:
             states = torch.zeros((nstreams, STATE_WORDS), dtype=torch.int32, device=samples.device)
-        rc = lib().fsk_b200_rx_batch(self._e, _ptr(samples), nstreams, stride, _ptr(nsamples_each), n_all,
-                                     _ptr(frames), max_frames, _ptr(states), _stream_handle(stream))
+        # int16 rows: fsk_b200_rx_batch_s16 (the PCM samples are widened inside the kernel's ring fill)
+        fn = lib().fsk_b200_rx_batch if samples.dtype == torch.float32 else lib().fsk_b200_rx_batch_s16
+        rc = fn(self._e, _ptr(samples), nstreams, stride, _ptr(nsamples_each), n_all,
+                _ptr(frames), max_frames, _ptr(states), _stream_handle(stream))
         if rc:
             _err("fsk_b200_rx_batch", rc)
         return frames, states

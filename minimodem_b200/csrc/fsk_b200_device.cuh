@@ -1209,6 +1209,89 @@ __device__ __forceinline__ void ring_issue_bulk(const Ring rg, const float *__re
 	bulk_g2s(ring_s + rg.R * 4u, x + from + run1, m2 * 4u, bar);
 }
 
+/* ------------------------------------------------------------------------ */
+/* int16 PCM ingest fused into the fill (N2): a block's 128 samples arrive as 256  */
+/* bytes of int16 in the UPPER half of the block's own 512 bytes of ring, and are   */
+/* widened in place (x / 32768, exact) once they have landed                        */
+/* ------------------------------------------------------------------------ */
+/* the copies of one block: 16 chunks of 8 samples, chunk c -> bytes [256 + 16c, 272 + 16c) of the block */
+template <int G>
+__device__ __forceinline__ void ring_block16(unsigned ring_s, unsigned foff, const int16_t *__restrict__ src,
+	unsigned g)
+{
+#pragma unroll
+    for (int c0 = 0; c0 < 16; c0 += G) {
+	const unsigned c = (unsigned)c0 + g;
+	if (G <= 16 || c < 16u)
+	    ldgsts16(ring_s + foff * 4u + 256u + 16u * c, reinterpret_cast<const float *>(src + 8u * c));
+    }
+}
+/* the same for a block that reaches past the valid length n: bytes at or past n arrive as zeros */
+template <int G>
+__device__ __forceinline__ void ring_block16_tail(unsigned ring_s, unsigned foff, const int16_t *__restrict__ x,
+	unsigned n, unsigned first, unsigned g)
+{
+#pragma unroll
+    for (int c0 = 0; c0 < 16; c0 += G) {
+	const unsigned c = (unsigned)c0 + g;
+	if (G <= 16 || c < 16u) {
+	    const unsigned i = first + 8u * c;
+	    const unsigned valid = i + 8u <= n ? 16u : (i < n ? (n - i) * 2u : 0u);
+	    ldgsts16_zfill(ring_s + foff * 4u + 256u + 16u * c,
+		    reinterpret_cast<const float *>(valid ? x + i : x), valid);
+	}
+    }
+}
+/* widen a landed block in place: every lane reads its chunks (8 samples each), the group
+ * synchronises (a chunk's 32 bytes of floats may cover another chunk's 16 bytes of int16), then
+ * writes the floats, into the mirror behind the ring's end as well for the head of the ring */
+template <int G>
+__device__ __forceinline__ void ring_widen16(const Ring rg, unsigned foff, unsigned g, unsigned gmask)
+{
+    constexpr int CPL = G >= 16 ? 1 : 16 / G;
+    char *blk = static_cast<char *>(__cvta_shared_to_generic(rg.ring_s)) + (size_t)foff * 4u;
+    int4 v[CPL];
+#pragma unroll
+    for (int k = 0; k < CPL; k++) {
+	const unsigned c = (unsigned)(k * G) + g;
+	if (G <= 16 || c < 16u)
+	    v[k] = *reinterpret_cast<const int4 *>(blk + 256u + 16u * c);
+    }
+    __syncwarp(gmask);
+#pragma unroll
+    for (int k = 0; k < CPL; k++) {
+	const unsigned c = (unsigned)(k * G) + g;
+	if (G <= 16 || c < 16u) {
+	    const float q = 1.0f / 32768.0f;		/* a power of two: the scaling is exact */
+	    float4 a, b;
+	    a.x = (float)(short)(v[k].x & 0xffff) * q;  a.y = (float)(short)(v[k].x >> 16) * q;
+	    a.z = (float)(short)(v[k].y & 0xffff) * q;  a.w = (float)(short)(v[k].y >> 16) * q;
+	    b.x = (float)(short)(v[k].z & 0xffff) * q;  b.y = (float)(short)(v[k].z >> 16) * q;
+	    b.z = (float)(short)(v[k].w & 0xffff) * q;  b.w = (float)(short)(v[k].w >> 16) * q;
+	    float4 *d = reinterpret_cast<float4 *>(blk + 32u * c);
+	    d[0] = a;
+	    d[1] = b;
+	    if (foff + 8u * c < rg.pad) {		/* pad % 4 == 0: a float4 is mirrored whole or not at all */
+		float4 *m = reinterpret_cast<float4 *>(blk + (size_t)rg.R * 4u + 32u * c);
+		m[0] = a;
+		if (foff + 8u * c + 4u < rg.pad)
+		    m[1] = b;
+	    }
+	}
+    }
+    __syncwarp(gmask);
+}
+
+/* int16 streams straight from global memory (generic path) */
+struct GlobalSrc16 {
+    const int16_t *x;
+    unsigned n;
+    __device__ __forceinline__ float operator()(unsigned i) const
+    {
+	return i < n ? (float)__ldg(x + i) * (1.0f / 32768.0f) : 0.0f;
+    }
+};
+
 /* plain zero fill of absolute indices [from, to) (any alignment) by the group */
 template <int G>
 __device__ __forceinline__ void ring_zero(const Ring rg, unsigned pos, unsigned pos_off,

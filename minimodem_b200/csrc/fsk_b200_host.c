@@ -656,6 +656,33 @@ int fsk_b200_rx_batch(fsk_b200_engine *e, const float *samples, size_t nstreams,
 	    nsamples, nsamples_all, frames, max_frames, states, stream);
 }
 
+int fsk_b200_rx_batch_s16(fsk_b200_engine *e, const int16_t *samples, size_t nstreams, size_t stride,
+	const uint32_t *nsamples, uint32_t nsamples_all, fsk_b200_frame *frames,
+	uint32_t max_frames, fsk_b200_stream_state *states, void *stream)
+{
+    if (nstreams == 0)
+	return 0;
+    if (!samples || ((uintptr_t)samples & 15) || (stride & 7)) {
+	fsk_b200_set_error("rx_batch_s16: samples must be 16-byte aligned and stride a multiple of 8 samples");
+	return -EINVAL;
+    }
+    if (!frames || !states || max_frames == 0) {
+	fsk_b200_set_error("rx_batch_s16: NULL argument");
+	return -EINVAL;
+    }
+    if ((!nsamples && (size_t)nsamples_all > stride) || nstreams > 0x7fffffffu) {
+	fsk_b200_set_error("rx_batch_s16: nsamples_all (%u) exceeds the row stride (%zu), or too many streams",
+		nsamples_all, stride);
+	return -EINVAL;
+    }
+    int rc = fsk_b200_cuda_rx_batch_s16(e->ce, &e->geom, &e->loopc, samples, nstreams, stride,
+	    nsamples, nsamples_all, frames, max_frames, states, stream);
+    if (rc == -ENOTSUP)
+	fsk_b200_set_error("rx_batch_s16: this mode's launch shape has no int16 build; widen with fsk_b200_s16_to_f32 "
+		"and call fsk_b200_rx_batch (fsk_b200_rx_batch_host_s16 does that by itself)");
+    return rc;
+}
+
 /* ---- live streams ------------------------------------------------------------ */
 
 uint32_t fsk_b200_stream_window(const fsk_b200_rx_params *p)

@@ -95,6 +95,10 @@ int  fsk_b200_cuda_rx_batch(void *ce, const fsk_b200_geom *g, const fsk_b200_loo
 	const float *samples, size_t nstreams, size_t stride, const uint32_t *nsamples,
 	uint32_t nsamples_all, fsk_b200_frame *frames, uint32_t max_frames,
 	fsk_b200_stream_state *states, void *stream);
+int  fsk_b200_cuda_rx_batch_s16(void *ce, const fsk_b200_geom *g, const fsk_b200_loopc *lc,
+	const int16_t *samples, size_t nstreams, size_t stride, const uint32_t *nsamples,
+	uint32_t nsamples_all, fsk_b200_frame *frames, uint32_t max_frames,
+	fsk_b200_stream_state *states, void *stream);
 int  fsk_b200_cuda_rx_batch_host(void *ce, const fsk_b200_geom *g, const fsk_b200_loopc *lc,
 	const float *host_samples, size_t nstreams, size_t stride, uint32_t nsamples_all,
 	fsk_b200_frame *host_frames, uint32_t max_frames, fsk_b200_stream_state *host_states);

@@ -115,6 +115,7 @@ struct FindArgs {
 
 struct RxArgs {
     const float *samples;
+    const int16_t *samples16;	/* SRC 1: the same rows as int16 PCM (x / 32768), `samples` unused */
     unsigned nstreams;
     size_t stride;
     const uint32_t *nsamples;
@@ -219,7 +220,9 @@ k_find_frame(const __grid_constant__ fsk_b200_geom geo, const float4 *__restrict
 #ifndef FSK_MAXTHREADS
 #define FSK_MAXTHREADS 128
 #endif
-template <int G, int W, int L, int MODE, int FILL>
+/* SRC 0: float32 rows; SRC 1: int16 PCM rows (N2, src/simpleaudio-sndfile.c:43-57), widened to the
+ * reference's float = short / 32768 inside the ring fill: 2 bytes per sample of HBM traffic */
+template <int G, int W, int L, int MODE, int FILL, int SRC = 0>
 __global__ void __launch_bounds__(FSK_MAXTHREADS, (MODE == 2 && G >= 16) ? 3 : FSK_MINBLOCKS)
 k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200_loopc lc,
 	const float4 *__restrict__ tw_global, unsigned tw_in_smem, unsigned ring_floats,
@@ -240,10 +243,13 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
 	fsk_b200_stream_state st = a.states[s];
 	if (st.done)
 	    continue;
-	const float *x = a.samples + (size_t)s * a.stride;
+	const float *x = SRC ? (const float *)nullptr : a.samples + (size_t)s * a.stride;
+	const int16_t *x16 = SRC ? a.samples16 + (size_t)s * a.stride : (const int16_t *)nullptr;
 	/* a row never extends past its stride (per-stream lengths are caller data) */
 	const unsigned n = (unsigned)min((size_t)(a.nsamples ? a.nsamples[s] : a.nsamples_all), a.stride);
 	fsk_b200_frame *out = a.frames + (size_t)s * a.max_frames;
+	/* 16-byte chunks of the source line up with 16-byte chunks of the ring: 4 floats, or 8 int16 */
+	constexpr unsigned AL = SRC ? 7u : 3u;
 
 	unsigned pos = (unsigned)st.pos;
 	unsigned nframes = st.nframes;
@@ -258,8 +264,9 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
 
 	/* ring bookkeeping (MODE 0): ring offset of `pos`, and the absolute index up to
 	 * which the ring content has been REQUESTED (copies issued or zeros stored) */
-	unsigned pos_off = pos & 3u;
-	unsigned filled = pos & ~3u;
+	unsigned pos_off = pos & AL;
+	unsigned filled = pos & ~AL;
+	unsigned conv = filled, coff = 0;		/* SRC 1: blocks up to `conv` (ring offset coff) are widened */
 	const unsigned need_max = lc.try_max_nocarrier - 1u + geo.span;
 	const unsigned n4 = (n + 3u) & ~3u;		/* rows are readable up to a multiple of 4 */
 	const unsigned bar0 = smem_u32(sm.bars), bar1 = bar0 + 8u;
@@ -267,20 +274,25 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
 	bool tail_fix = false;				/* bulk fill: [n, n4) holds row padding, not zeros */
 
 	const unsigned ring_s = rg.ring_s;
-	unsigned landed = pos & ~3u;			/* absolute index up to which copies are known to have landed */
+	unsigned landed = pos & ~AL;			/* absolute index up to which copies are known to have landed */
 	/* block fill: this lane's running source and destination (its first 16-byte chunk of
 	 * the block that starts at absolute index `filled`), carried instead of recomputed */
 	const unsigned dst0 = ring_s + 16u * g, dst_end = dst0 + R * 4u;
 	const unsigned mlim = ring_s + rg.pad * 4u;	/* chunks below this are mirrored behind the end */
 	unsigned fdst = dst0;
-	const float *fsrc = x + filled + 4u * g;
+	const float *fsrc = SRC ? x : x + filled + 4u * g;
 	/* request the ring content up to absolute index `to` (rounded up to whole blocks) */
 	auto request_at = [&](unsigned to, unsigned base) {
 	    /* FILL 0 only: whole blocks while they start below `to` and still fit in a ring
 	     * whose oldest live sample is `base` */
-	    const unsigned lim = min(to, (base & ~3u) + R - (RING_BLOCK - 1u));
+	    const unsigned lim = min(to, (base & ~AL) + R - (RING_BLOCK - 1u));
 	    while (filled < lim) {
-		if (filled + RING_BLOCK <= n)		/* the common case: all of it valid */
+		if (SRC) {				/* int16 rows: landing zone = upper half of the block */
+		    if (filled + RING_BLOCK <= n)
+			ring_block16<G>(ring_s, (fdst - dst0) >> 2, x16 + filled, g);
+		    else
+			ring_block16_tail<G>(ring_s, (fdst - dst0) >> 2, x16, n, filled, g);
+		} else if (filled + RING_BLOCK <= n)	/* the common case: all of it valid */
 		    ring_block_at<G>(fdst, fsrc, mlim, R);
 		else					/* end of the stream: zero fill */
 		    ring_block_tail<G>(rg, ring_s, (fdst - dst0) >> 2, x, n, filled, g);
@@ -360,7 +372,7 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
 		}
 	    }
 	    __syncwarp(gmask);
-	    request(min((pos + need_max + 3u) & ~3u, (pos & ~3u) + R));
+	    request(min((pos + need_max + 3u) & ~3u, (pos & ~AL) + R));
 	}
 
 	for (;;) {
@@ -390,9 +402,22 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
 		 * requests made since -- the early one and the one below -- are still in flight */
 		ready = (int)(landed - pos);
 		if (FILL != 0 || !EARLY_REQ || late)	/* EARLY_REQ: normally asked for an iteration ago */
-		    request(min((pos + lookahead + need_max + 3u) & ~3u, (pos & ~3u) + R));
+		    request(min((pos + lookahead + need_max + 3u) & ~3u, (pos & ~AL) + R));
 		landed = filled;			/* true once this iteration's search has waited */
-		if (FILL == 0) {
+		if (SRC) {
+		    /* int16 rows: everything requested so far has to land and be widened in place
+		     * before the search reads it (the float fill lets the search itself wait) */
+		    cp_async_wait<0>();
+		    __syncwarp(gmask);
+		    while (conv < filled) {
+			ring_widen16<G>(rg, coff, g, gmask);
+			conv += RING_BLOCK;
+			coff += RING_BLOCK;
+			if (coff == R)
+			    coff = 0;
+		    }
+		    pending = false;
+		} else if (FILL == 0) {
 #if FSK_STAGE_J < 8
 		    settle(false);	/* two-stage correlation: the first stage needs the older copies */
 		    pending = true;
@@ -405,6 +430,7 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
 		    settle(late);
 	    }
 	    const GlobalSrc gsrc = { x, n };
+	    const GlobalSrc16 gsrc16 = { x16, n };
 
 	    unsigned long long bits;
 	    float amplitude, confidence;
@@ -493,12 +519,16 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
 		    const unsigned adv = c <= lc.confidence_threshold ? try_max
 			    : fs + lc.frame_nsamples - lc.nsamples_overscan;
 		    const unsigned npos = pos + adv;
-		    if (adv <= remaining && filled >= (npos & ~3u)) {
+		    if (adv <= remaining && filled >= (npos & ~AL)) {
 			__syncwarp(gmask);	/* every read of this window precedes the copies */
-			request_at(min((npos + lookahead + need_max + 3u) & ~3u, (npos & ~3u) + R), npos);
+			request_at(min((npos + lookahead + need_max + 3u) & ~3u, (npos & ~AL) + R), npos);
 		    }
 		}
-	    } else
+	    } else if (SRC)
+		confidence = find_frame<G, GlobalSrc16>(gsrc16, pos, geo, sel, sm.tw, sm.scr, g, gmask,
+			try_first, try_max, try_step, lc.confidence_search_limit,
+			bits, amplitude, frame_start);
+	    else
 		confidence = find_frame<G, GlobalSrc>(gsrc, pos, geo, sel, sm.tw, sm.scr, g, gmask,
 			try_first, try_max, try_step, lc.confidence_search_limit,
 			bits, amplitude, frame_start);
@@ -553,7 +583,11 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
 			amplitude2 = refined.amplitude;
 			frame_start2 = refined.start;
 			bits2 = ((unsigned long long)refined.bits_hi << 32) | refined.bits_lo;
-		    } else
+		    } else if (SRC)
+			confidence2 = find_frame<G, GlobalSrc16>(gsrc16, pos, geo, 0, sm.tw, sm.scr, g,
+				gmask, try_first, try_max, try_step, INFINITY,
+				bits2, amplitude2, frame_start2);
+		    else
 			confidence2 = find_frame<G, GlobalSrc>(gsrc, pos, geo, 0, sm.tw, sm.scr, g,
 				gmask, try_first, try_max, try_step, INFINITY,
 				bits2, amplitude2, frame_start2);
@@ -579,14 +613,16 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
 	    pos += advance;
 	    if (MODE != 1) {
 		pos_off = ring_wrap(pos_off + advance, R);	/* advance < R by construction */
-		if (filled < (pos & ~3u)) {
+		if (filled < (pos & ~AL)) {
 		    /* skipped past everything requested so far: restart the ring here */
 		    drain();
-		    filled = pos & ~3u;
+		    filled = pos & ~AL;
 		    landed = filled;
-		    pos_off = pos & 3u;
+		    pos_off = pos & AL;
 		    fdst = dst0;
-		    fsrc = x + filled + 4u * g;
+		    fsrc = SRC ? x : x + filled + 4u * g;
+		    conv = filled;
+		    coff = 0;
 		}
 		__syncwarp(gmask);	/* every read of this window precedes the next copies */
 	    }
@@ -1100,8 +1136,9 @@ struct CudaEngine {
     float *d_mags;
     size_t d_mags_cap;
     /* host-batch slabs */
-    float *d_slab[2];
-    int16_t *d_slab_s16[2];
+    float *d_slab[2];			/* float32 copy of an int16 slab (only when the widening is a separate pass) */
+    void *d_slab_in[2];			/* the slab as it came over the wire: float32 or int16 */
+    size_t slab_in_bytes, slab_f32_floats;
     fsk_b200_frame *d_slab_frames[2];
     fsk_b200_stream_state *d_slab_states[2];
     size_t slab_streams, slab_stride, slab_max_frames;
@@ -1181,7 +1218,7 @@ extern "C" void fsk_b200_cuda_engine_destroy(void *p)
     cudaFree(ce->d_mags);
     for (int i = 0; i < 2; i++) {
 	cudaFree(ce->d_slab[i]);
-	cudaFree(ce->d_slab_s16[i]);
+	cudaFree(ce->d_slab_in[i]);
 	cudaFree(ce->d_slab_frames[i]);
 	cudaFree(ce->d_slab_states[i]);
 	if (ce->st[i])
@@ -1295,6 +1332,11 @@ struct Shape {
 #define MULTI_COMBOS(X) \
     X(8, 2, 2) X(8, 3, 2) X(8, 4, 2) X(16, 2, 2) X(16, 3, 2) X(16, 4, 2) X(16, 2, 4) X(16, 3, 4) X(16, 4, 4) \
     X(32, 2, 4) X(32, 3, 4) X(32, 4, 4)
+
+/* per-candidate shapes that are also built for int16 rows (SRC 1); every MULTI_COMBOS shape is */
+#define S16_FAST_COMBOS(X) \
+    X(8, 1, 1) X(8, 2, 1) X(8, 3, 1) X(8, 2, 2) X(8, 3, 2) X(8, 4, 2) X(8, 4, 4) \
+    X(16, 1, 2) X(16, 2, 2) X(16, 2, 4) X(16, 3, 4) X(16, 4, 4) X(32, 2, 4)
 
 /* the alternative kernels (TMA bulk fill, group-masked loop) are built for the shapes the
  * defaults pick for the BASELINE configurations only */
@@ -1519,26 +1561,27 @@ static cudaError_t launch_rx_ws_t(const Shape &sh, const CudaEngine *ce, const f
     return cudaGetLastError();
 }
 
-template <int G, int W, int L, int MODE, int FILL>
+template <int G, int W, int L, int MODE, int FILL, int SRC = 0>
 static cudaError_t launch_rx_t(const Shape &sh, const CudaEngine *ce, const fsk_b200_loopc *lc,
 	const RxArgs &a, cudaStream_t st)
 {
-    cudaError_t e = cudaFuncSetAttribute(k_rx<G, W, L, MODE, FILL>,
+    cudaError_t e = cudaFuncSetAttribute(k_rx<G, W, L, MODE, FILL, SRC>,
 	    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh.smem);
     if (e != cudaSuccess)
 	return e;
-    FSK_LAUNCH((k_rx<G, W, L, MODE, FILL>), sh.blocks, sh.wpb * 32, sh.smem, st, sh.geo, *lc, ce->d_tw,
+    FSK_LAUNCH((k_rx<G, W, L, MODE, FILL, SRC>), sh.blocks, sh.wpb * 32, sh.smem, st, sh.geo, *lc, ce->d_tw,
 	    sh.tw_in_smem, sh.ring, sh.lookahead, a, sh.mplan);
     g_launches++;
     return cudaGetLastError();
 }
 
-extern "C" int fsk_b200_cuda_rx_batch(void *p, const fsk_b200_geom *g, const fsk_b200_loopc *lc,
-	const float *samples, size_t nstreams, size_t stride, const uint32_t *nsamples,
+/* elem 4: float32 rows; elem 2: int16 PCM rows, widened inside the kernel's ring fill.  -ENOTSUP when
+ * the launch shape of this mode has no int16 build (the caller widens with fsk_b200_cuda_s16_to_f32). */
+static int rx_batch_any(CudaEngine *ce, const fsk_b200_geom *g, const fsk_b200_loopc *lc,
+	const void *samples, int elem, size_t nstreams, size_t stride, const uint32_t *nsamples,
 	uint32_t nsamples_all, fsk_b200_frame *frames, uint32_t max_frames,
 	fsk_b200_stream_state *states, void *stream)
 {
-    CudaEngine *ce = (CudaEngine *)p;
     if (!ce->d_tw || ce->tw_n < g->bit_nsamples) {
 	fsk_b200_set_error("rx_batch: twiddle table not set");
 	return -EINVAL;
@@ -1550,11 +1593,29 @@ extern "C" int fsk_b200_cuda_rx_batch(void *p, const fsk_b200_geom *g, const fsk
 	? lc->try_max_nocarrier : lc->try_max_carrier;
     const unsigned max_advance = tmax - 1u + lc->frame_nsamples;	/* :1407, overscan >= 0 */
     pick_shape(ce, g, tmax - 1u + g->span, max_advance, nstreams, &sh, lc);
-    const RxArgs a = { samples, (unsigned)nstreams, stride, nsamples, nsamples_all, frames, max_frames,
-	states };
+    const RxArgs a = { elem == 4 ? (const float *)samples : NULL, elem == 2 ? (const int16_t *)samples : NULL,
+	(unsigned)nstreams, stride, nsamples, nsamples_all, frames, max_frames, states };
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e = cudaErrorInvalidValue;
-    if (sh.mode == 2) {
+    bool launched = false;
+    if (elem == 2) {
+	if (ce->fill != 0)
+	    return -ENOTSUP;
+	if (sh.mode == 2) {
+#define X(GG, WW, LL) if (sh.G == GG && sh.W == WW && sh.L == LL) { e = launch_rx_t<GG, WW, LL, 2, 0, 1>(sh, ce, lc, a, st); launched = true; }
+	    MULTI_COMBOS(X)
+#undef X
+	} else if (sh.mode == 0) {
+#define X(GG, WW, LL) if (sh.G == GG && sh.W == WW && sh.L == LL) { e = launch_rx_t<GG, WW, LL, 0, 0, 1>(sh, ce, lc, a, st); launched = true; }
+	    S16_FAST_COMBOS(X)
+#undef X
+	} else {
+	    e = launch_rx_t<32, 1, 1, 1, 0, 1>(sh, ce, lc, a, st);
+	    launched = true;
+	}
+	if (!launched)
+	    return -ENOTSUP;
+    } else if (sh.mode == 2) {
 #define X(GG, WW, LL) if (sh.G == GG && sh.W == WW && sh.L == LL) e = launch_rx_t<GG, WW, LL, 2, 0>(sh, ce, lc, a, st);
 	MULTI_COMBOS(X)
 #undef X
@@ -1563,7 +1624,6 @@ extern "C" int fsk_b200_cuda_rx_batch(void *p, const fsk_b200_geom *g, const fsk
 	 * (UBLKCP + mbarrier); 3 cp.async fill, warp-synchronous loop.  The two alternatives
 	 * pass the same tests and measured slower (profiles/README.md); they are built for the
 	 * shapes of the BASELINE configurations only. */
-	bool launched = false;
 	if (ce->fill == 1) {
 #define X(GG, WW, LL) if (sh.G == GG && sh.W == WW && sh.L == LL) { e = launch_rx_t<GG, WW, LL, 0, 1>(sh, ce, lc, a, st); launched = true; }
 	    ALT_COMBOS(X)
@@ -1582,9 +1642,9 @@ extern "C" int fsk_b200_cuda_rx_batch(void *p, const fsk_b200_geom *g, const fsk
 	e = launch_rx_t<32, 1, 1, 1, 0>(sh, ce, lc, a, st);
     }
     snprintf(ce->last_kernel, sizeof(ce->last_kernel),
-	    "k_rx<G=%d,W=%d,L=%d,mode=%d(%s),fill=%d> threads=%d ring=%u smem=%zu blocks=%d", sh.G, sh.W, sh.L, sh.mode,
-	    sh.mode == 2 ? "shared-segment" : sh.mode == 0 ? "per-candidate" : "generic", sh.mode == 0 ? ce->fill : 0,
-	    sh.wpb * 32, sh.ring, sh.smem, sh.blocks);
+	    "k_rx<G=%d,W=%d,L=%d,mode=%d(%s),fill=%d,src=%s> threads=%d ring=%u smem=%zu blocks=%d", sh.G, sh.W, sh.L,
+	    sh.mode, sh.mode == 2 ? "shared-segment" : sh.mode == 0 ? "per-candidate" : "generic",
+	    sh.mode == 0 ? ce->fill : 0, elem == 2 ? "s16" : "f32", sh.wpb * 32, sh.ring, sh.smem, sh.blocks);
     if (e != cudaSuccess) {
 	fsk_b200_set_error("rx_batch launch (G=%d W=%d L=%d mode=%d ring=%u smem=%zu): %s", sh.G, sh.W,
 		sh.L, sh.mode, sh.ring, sh.smem, cudaGetErrorString(e));
@@ -1593,66 +1653,154 @@ extern "C" int fsk_b200_cuda_rx_batch(void *p, const fsk_b200_geom *g, const fsk
     return 0;
 }
 
-/* host buffers in, host results out: slabs of streams, copy/compute overlap.
- * elem = 4: float32 samples; elem = 2: int16 samples, widened on the device. */
+extern "C" int fsk_b200_cuda_rx_batch(void *p, const fsk_b200_geom *g, const fsk_b200_loopc *lc,
+	const float *samples, size_t nstreams, size_t stride, const uint32_t *nsamples,
+	uint32_t nsamples_all, fsk_b200_frame *frames, uint32_t max_frames,
+	fsk_b200_stream_state *states, void *stream)
+{
+    return rx_batch_any((CudaEngine *)p, g, lc, samples, 4, nstreams, stride, nsamples, nsamples_all, frames,
+	    max_frames, states, stream);
+}
+
+extern "C" int fsk_b200_cuda_rx_batch_s16(void *p, const fsk_b200_geom *g, const fsk_b200_loopc *lc,
+	const int16_t *samples, size_t nstreams, size_t stride, const uint32_t *nsamples,
+	uint32_t nsamples_all, fsk_b200_frame *frames, uint32_t max_frames,
+	fsk_b200_stream_state *states, void *stream)
+{
+    return rx_batch_any((CudaEngine *)p, g, lc, samples, 2, nstreams, stride, nsamples, nsamples_all, frames,
+	    max_frames, states, stream);
+}
+
+/* host buffers in, host results out: slabs of streams, copy/compute overlap on two streams.
+ * elem = 4: float32 samples; elem = 2: int16 PCM samples, which stay int16 in HBM and are widened
+ * inside the rx kernel's ring fill (rows 16-byte aligned, i.e. stride % 8 == 0, and a launch shape
+ * with an int16 build; otherwise a separate widening pass runs first).
+ * FSK_B200_TRACE=1 prints, per call, where the time went (CUDA events around every step). */
 static int rx_batch_host_common(CudaEngine *ce, const fsk_b200_geom *g, const fsk_b200_loopc *lc,
 	const void *host_samples, int elem, size_t nstreams, size_t stride, uint32_t nsamples_all,
 	fsk_b200_frame *host_frames, uint32_t max_frames, fsk_b200_stream_state *host_states)
 {
+    if (engine_device_check(ce, "rx_batch_host"))
+	return -EINVAL;
     /* slab = as many streams as make slab_bytes on the wire (two slabs in flight) */
     size_t slab = ce->slab_bytes / (stride * (size_t)elem);
     if (slab < 1) slab = 1;
     if (slab > nstreams) slab = nstreams;
-    if (ce->slab_streams < slab || ce->slab_stride != stride || ce->slab_max_frames < max_frames) {
-	/* forget the old shape first: a failed allocation below must not leave it looking valid */
-	ce->slab_streams = ce->slab_stride = ce->slab_max_frames = 0;
-	for (int i = 0; i < 2; i++) {
-	    cudaFree(ce->d_slab[i]); ce->d_slab[i] = NULL;
-	    cudaFree(ce->d_slab_frames[i]); ce->d_slab_frames[i] = NULL;
-	    cudaFree(ce->d_slab_states[i]); ce->d_slab_states[i] = NULL;
-	    cudaFree(ce->d_slab_s16[i]); ce->d_slab_s16[i] = NULL;
-	    CUDA_TRY(cudaMalloc(&ce->d_slab[i], slab * stride * sizeof(float)));
-	    CUDA_TRY(cudaMalloc(&ce->d_slab_frames[i], slab * (size_t)max_frames * sizeof(fsk_b200_frame)));
-	    CUDA_TRY(cudaMalloc(&ce->d_slab_states[i], slab * sizeof(fsk_b200_stream_state)));
-	    if (!ce->st[i])
-		CUDA_TRY(cudaStreamCreateWithFlags(&ce->st[i], cudaStreamNonBlocking));
+    bool fused = elem == 2 && (stride & 7) == 0 && ce->fill == 0;
+    int rc = 0;
+#define HOST_TRY(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+	fsk_b200_set_error("%s: %s", #call, cudaGetErrorString(e_)); rc = -EIO; goto fail; } } while (0)
+    {
+	const size_t need_bytes = slab * stride * (size_t)elem;
+	if (ce->slab_streams < slab || ce->slab_stride != stride || ce->slab_max_frames < max_frames
+		|| ce->slab_in_bytes < need_bytes) {
+	    /* forget the old shape first: a failed allocation below must not leave it looking valid */
+	    ce->slab_streams = ce->slab_stride = ce->slab_max_frames = 0;
+	    ce->slab_in_bytes = ce->slab_f32_floats = 0;
+	    for (int i = 0; i < 2; i++) {
+		cudaFree(ce->d_slab[i]); ce->d_slab[i] = NULL;
+		cudaFree(ce->d_slab_in[i]); ce->d_slab_in[i] = NULL;
+		cudaFree(ce->d_slab_frames[i]); ce->d_slab_frames[i] = NULL;
+		cudaFree(ce->d_slab_states[i]); ce->d_slab_states[i] = NULL;
+		HOST_TRY(cudaMalloc(&ce->d_slab_in[i], need_bytes));
+		HOST_TRY(cudaMalloc(&ce->d_slab_frames[i], slab * (size_t)max_frames * sizeof(fsk_b200_frame)));
+		HOST_TRY(cudaMalloc(&ce->d_slab_states[i], slab * sizeof(fsk_b200_stream_state)));
+		if (!ce->st[i])
+		    HOST_TRY(cudaStreamCreateWithFlags(&ce->st[i], cudaStreamNonBlocking));
+	    }
+	    ce->slab_streams = slab;
+	    ce->slab_stride = stride;
+	    ce->slab_max_frames = max_frames;
+	    ce->slab_in_bytes = need_bytes;
 	}
-	ce->slab_streams = slab;
-	ce->slab_stride = stride;
-	ce->slab_max_frames = max_frames;
     }
-    if (elem == 2)
-	for (int i = 0; i < 2; i++)
-	    if (!ce->d_slab_s16[i])
-		CUDA_TRY(cudaMalloc(&ce->d_slab_s16[i], ce->slab_streams * stride * sizeof(int16_t)));
-    int k = 0;
-    for (size_t s0 = 0; s0 < nstreams; s0 += slab, k ^= 1) {
-	const size_t ns = nstreams - s0 < slab ? nstreams - s0 : slab;
-	cudaStream_t st = ce->st[k];
-	if (elem == 4) {
-	    CUDA_TRY(cudaMemcpyAsync(ce->d_slab[k], (const float *)host_samples + s0 * stride,
-			ns * stride * sizeof(float), cudaMemcpyHostToDevice, st));
-	} else {
-	    CUDA_TRY(cudaMemcpyAsync(ce->d_slab_s16[k], (const int16_t *)host_samples + s0 * stride,
-			ns * stride * sizeof(int16_t), cudaMemcpyHostToDevice, st));
-	    int rc = fsk_b200_cuda_s16_to_f32(ce->d_slab_s16[k], ce->d_slab[k], ns, stride, st);
+    {
+	const bool trace = getenv("FSK_B200_TRACE") != NULL;
+	const size_t nslabs = (nstreams + slab - 1) / slab;
+	cudaEvent_t *ev = NULL;		/* per slab: start, after H2D, after kernel, after D2H */
+	if (trace) {
+	    ev = (cudaEvent_t *)calloc(nslabs * 4, sizeof(cudaEvent_t));
+	    for (size_t i = 0; ev && i < nslabs * 4; i++)
+		cudaEventCreate(&ev[i]);
+	}
+	int k = 0;
+	size_t si = 0;
+	for (size_t s0 = 0; s0 < nstreams; s0 += slab, k ^= 1, si++) {
+	    const size_t ns = nstreams - s0 < slab ? nstreams - s0 : slab;
+	    cudaStream_t st = ce->st[k];
+	    if (ev) cudaEventRecord(ev[4 * si], st);
+	    HOST_TRY(cudaMemcpyAsync(ce->d_slab_in[k], (const char *)host_samples + s0 * stride * (size_t)elem,
+			ns * stride * (size_t)elem, cudaMemcpyHostToDevice, st));
+	    HOST_TRY(cudaMemcpyAsync(ce->d_slab_states[k], host_states + s0, ns * sizeof(fsk_b200_stream_state),
+			cudaMemcpyHostToDevice, st));
+	    if (ev) cudaEventRecord(ev[4 * si + 1], st);
+	    if (elem == 4) {
+		rc = rx_batch_any(ce, g, lc, ce->d_slab_in[k], 4, ns, stride, NULL, nsamples_all,
+			ce->d_slab_frames[k], max_frames, ce->d_slab_states[k], st);
+	    } else {
+		rc = fused ? rx_batch_any(ce, g, lc, ce->d_slab_in[k], 2, ns, stride, NULL, nsamples_all,
+			ce->d_slab_frames[k], max_frames, ce->d_slab_states[k], st) : -ENOTSUP;
+		if (rc == -ENOTSUP) {		/* no int16 build for this mode's launch shape: widen first */
+		    fused = false;
+		    if (ce->slab_f32_floats < slab * stride) {
+			for (int i = 0; i < 2; i++) {
+			    cudaFree(ce->d_slab[i]); ce->d_slab[i] = NULL;
+			}
+			ce->slab_f32_floats = 0;
+			for (int i = 0; i < 2; i++)
+			    HOST_TRY(cudaMalloc(&ce->d_slab[i], slab * stride * sizeof(float)));
+			ce->slab_f32_floats = slab * stride;
+		    }
+		    rc = fsk_b200_cuda_s16_to_f32((const int16_t *)ce->d_slab_in[k], ce->d_slab[k], ns, stride, st);
+		    if (!rc)
+			rc = rx_batch_any(ce, g, lc, ce->d_slab[k], 4, ns, stride, NULL, nsamples_all,
+				ce->d_slab_frames[k], max_frames, ce->d_slab_states[k], st);
+		}
+	    }
 	    if (rc)
-		return rc;
+		goto fail;
+	    if (ev) cudaEventRecord(ev[4 * si + 2], st);
+	    HOST_TRY(cudaMemcpyAsync(host_frames + s0 * (size_t)max_frames, ce->d_slab_frames[k],
+			ns * (size_t)max_frames * sizeof(fsk_b200_frame), cudaMemcpyDeviceToHost, st));
+	    HOST_TRY(cudaMemcpyAsync(host_states + s0, ce->d_slab_states[k], ns * sizeof(fsk_b200_stream_state),
+			cudaMemcpyDeviceToHost, st));
+	    if (ev) cudaEventRecord(ev[4 * si + 3], st);
 	}
-	CUDA_TRY(cudaMemcpyAsync(ce->d_slab_states[k], host_states + s0, ns * sizeof(fsk_b200_stream_state),
-		    cudaMemcpyHostToDevice, st));
-	int rc = fsk_b200_cuda_rx_batch(ce, g, lc, ce->d_slab[k], ns, stride, NULL, nsamples_all,
-		ce->d_slab_frames[k], max_frames, ce->d_slab_states[k], st);
-	if (rc)
-	    return rc;
-	CUDA_TRY(cudaMemcpyAsync(host_frames + s0 * (size_t)max_frames, ce->d_slab_frames[k],
-		    ns * (size_t)max_frames * sizeof(fsk_b200_frame), cudaMemcpyDeviceToHost, st));
-	CUDA_TRY(cudaMemcpyAsync(host_states + s0, ce->d_slab_states[k], ns * sizeof(fsk_b200_stream_state),
-		    cudaMemcpyDeviceToHost, st));
+	HOST_TRY(cudaStreamSynchronize(ce->st[0]));
+	HOST_TRY(cudaStreamSynchronize(ce->st[1]));
+	if (ev) {
+	    float h2d = 0, kern = 0, d2h = 0, wall = 0, gap = 0, t;
+	    for (size_t i = 0; i < nslabs; i++) {
+		cudaEventElapsedTime(&t, ev[4 * i], ev[4 * i + 1]); h2d += t;
+		cudaEventElapsedTime(&t, ev[4 * i + 1], ev[4 * i + 2]); kern += t;
+		cudaEventElapsedTime(&t, ev[4 * i + 2], ev[4 * i + 3]); d2h += t;
+		if (i + 1 < nslabs) {	/* end of this slab's H2D to the end of the next one's, minus its duration */
+		    float nx;
+		    cudaEventElapsedTime(&t, ev[4 * i + 1], ev[4 * (i + 1) + 1]);
+		    cudaEventElapsedTime(&nx, ev[4 * (i + 1)], ev[4 * (i + 1) + 1]);
+		    (void)nx;
+		    gap += t;
+		}
+	    }
+	    cudaEventElapsedTime(&wall, ev[0], ev[4 * (nslabs - 1) + 3]);
+	    fprintf(stderr, "fsk_b200 trace: %zu slabs of %zu streams (%s%s): wall %.2f ms; per slab: H2D+state %.3f ms, "
+		    "kernel(s) %.3f ms, D2H %.3f ms; H2D-end to H2D-end %.3f ms; wire %.2f GB/s\n", nslabs, slab,
+		    elem == 2 ? "int16" : "float32", elem == 2 ? (fused ? ", widened in the rx kernel" : ", separate widening pass") : "",
+		    wall, h2d / nslabs, kern / nslabs, d2h / nslabs, nslabs > 1 ? gap / (nslabs - 1) : 0.f,
+		    (double)nstreams * stride * elem / (wall * 1e6));
+	    for (size_t i = 0; i < nslabs * 4; i++)
+		cudaEventDestroy(ev[i]);
+	    free(ev);
+	}
     }
-    CUDA_TRY(cudaStreamSynchronize(ce->st[0]));
-    CUDA_TRY(cudaStreamSynchronize(ce->st[1]));
     return 0;
+fail:
+    /* nothing of this call may still be writing into the caller's buffers when it returns */
+    if (ce->st[0]) cudaStreamSynchronize(ce->st[0]);
+    if (ce->st[1]) cudaStreamSynchronize(ce->st[1]);
+    (void)cudaGetLastError();
+    return rc;
+#undef HOST_TRY
 }
 
 extern "C" int fsk_b200_cuda_rx_batch_host(void *p, const fsk_b200_geom *g, const fsk_b200_loopc *lc,

@@ -1150,3 +1150,64 @@ def test_baseline_configs_large_batch_sample_vs_oracle(mode, kw, nstreams, nword
             n_flip += 1
             assert [orc.databits(m, f[0]) for f in got][:4] == [orc.databits(m, f[0]) for f in want["frames"]][:4]
     assert n_flip <= max(1, len(rows) // 50), (n_flip, len(rows))
+
+
+# --------------------------------------------------------------------------
+# N2 fused: int16 PCM rows resident in HBM, widened inside the rx kernel's ring fill
+# (fsk_b200_rx_batch_s16) -- the records must be those of the float path on short/32768, bit for bit
+# --------------------------------------------------------------------------
+@pytest.mark.parametrize("mode,kw", [("1200", {}), ("300", {}), ("rtty", dict(sample_rate=8000)), ("same", {}),
+                                     ("0.5", dict(sample_rate=8000))],
+                         ids=["1200", "bell103", "rtty8k", "same", "generic-0.5baud"])
+def test_rx_batch_s16_resident_is_bit_identical_to_the_float_path(mode, kw):
+    m = orc.Mode(mode, **kw)
+    eng, cfg = engine_for((mode, kw))
+    rng = np.random.default_rng(16)
+    nstreams = 21
+    nwords = 3 if mode == "0.5" else 30
+    rows, lens = [], []
+    for s in range(nstreams):
+        lo, hi = (32, 127) if m.n_data_bits >= 7 else (0, 1 << m.n_data_bits)
+        words = rng.integers(lo, hi, nwords, dtype=np.uint32)
+        x = orc.tx_words(m, words, 0.8, 4096, False)        # the transmitter's int16 samples, as floats / 32768
+        lead = 0 if cfg.do_rx_sync else int(rng.integers(0, 200))
+        x = np.concatenate([np.zeros(lead, np.float32), x, np.zeros(int(rng.integers(0, 300)), np.float32)])
+        if s % 5 == 4:
+            x = x[: x.size * 2 // 3]                       # ragged: cut in mid frame
+        rows.append(np.round(x * 32768.0).astype(np.int16))
+        lens.append(x.size)
+    n = max(lens)
+    stride = (n + 7) & ~7
+    pcm = np.zeros((nstreams, stride), np.int16)
+    for s, r in enumerate(rows):
+        pcm[s, :r.size] = r
+    lens_t = torch.from_numpy(np.asarray(lens, np.int32)).to(dev())
+    d16 = torch.from_numpy(pcm).to(dev())
+    f32 = mm.s16_to_f32(d16)
+    fr_a, st_a = eng.rx_batch(f32, nsamples=n, nsamples_each=lens_t)
+    fr_b, st_b = eng.rx_batch(d16, nsamples=n, nsamples_each=lens_t)
+    torch.cuda.synchronize()
+    assert "src=s16" in eng.last_kernel(), eng.last_kernel()
+    sa, sb = mm.states_to_numpy(st_a), mm.states_to_numpy(st_b)
+    for f in ("pos", "nframes", "carrier", "noconfidence", "done", "carrier_nsamples", "nframes_decoded"):
+        assert np.array_equal(sa[f], sb[f]), f
+    assert sa["nframes"].sum() > nstreams * (2 if mode == "0.5" else 10)
+    a, b = mm.frames_to_numpy(fr_a), mm.frames_to_numpy(fr_b)
+    for s in range(nstreams):
+        k = int(sa["nframes"][s])
+        assert a[s, :k].tobytes() == b[s, :k].tobytes(), (mode, s)
+    # resumed from a position that is not a multiple of 8 (the int16 fill aligns to 16 bytes = 8 samples)
+    st_c = st_b.clone()
+    st_c.zero_()
+    sc = mm.states_to_numpy(st_c).copy()
+    sc["pos"][:] = 13
+    st_c = torch.from_numpy(sc.view(np.int32).reshape(nstreams, -1)).to(dev())
+    st_d = st_c.clone()
+    fr_c, st_c = eng.rx_batch(f32, nsamples=n, nsamples_each=lens_t, states=st_c)
+    fr_d, st_d = eng.rx_batch(d16, nsamples=n, nsamples_each=lens_t, states=st_d)
+    torch.cuda.synchronize()
+    c, d = mm.frames_to_numpy(fr_c), mm.frames_to_numpy(fr_d)
+    sc2 = mm.states_to_numpy(st_c)
+    for s in range(nstreams):
+        k = int(sc2["nframes"][s])
+        assert c[s, :k].tobytes() == d[s, :k].tobytes(), (mode, s, "resumed")
