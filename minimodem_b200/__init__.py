@@ -10,7 +10,7 @@ raises otherwise.
 from .api import (  # noqa: F401
     LIB_PATH, Frame, RxConfig, RxParams, RxEngine, FskPlan, StreamState, TxConfig,
     build, lib, rx_config_for_mode, rx_params, frame_databits, max_frames, tx_batch,
-    version, launch_count, sin_table, frames_to_numpy, states_to_numpy, tx_config_from, s16_to_f32,
+    version, launch_count, sin_table, frames_to_numpy, states_to_numpy, check_not_truncated, tx_config_from, s16_to_f32,
     FRAME_DTYPE, STATE_DTYPE, STATE_WORDS, FRAME_ACQUIRED, FRAME_REPORT, EXPORTS,
     DECODE_ASCII, DECODE_BINARY, DECODE_BAUDOT, DECODE_CALLERID, DECODE_UIC_GROUND, DECODE_UIC_TRAIN,
     DECODER_STATE_BYTES, DecoderState, decoder_for_mode, decode_max_bytes_per_frame, decode_max_bytes, detect_carrier_batch, stream_push, wav_locate,

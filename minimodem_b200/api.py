@@ -560,8 +560,14 @@ def detect_carrier_batch(fftsize, samples, nsamples, min_mag_threshold, offset=N
 def stream_push(rows, fill, states, chunk, chunk_len=None, dropped=None, stream=None):
     """fsk_b200_stream_push on CUDA tensors: rows [n, stride] float32, fill [n] int32 (in/out), states
     [n, STATE_WORDS] int32 (in/out), chunk [n, chunk_stride] float32, chunk_len [n] int32 or an int."""
+    torch = _torch()
+    # the C call takes raw pointers and row strides: the tensors must be what it assumes
+    assert rows.is_contiguous() and rows.dtype == torch.float32 and chunk.is_contiguous() and chunk.dtype == torch.float32
+    assert fill.is_contiguous() and fill.dtype == torch.int32 and states.is_contiguous() and states.dtype == torch.int32
+    assert chunk.shape[0] == rows.shape[0] and states.shape == (rows.shape[0], STATE_WORDS)
     n, stride = rows.shape
     per = chunk_len if hasattr(chunk_len, "data_ptr") else None
+    assert per is None or (per.dtype == torch.int32 and per.is_contiguous())
     common = 0 if per is not None else int(chunk.shape[1] if chunk_len is None else chunk_len)
     rc = lib().fsk_b200_stream_push(_ptr(rows), n, stride, _ptr(fill), _ptr(states), _ptr(chunk),
                                     chunk.shape[1], _ptr(per), common, _ptr(dropped), _stream_handle(stream))
@@ -587,6 +593,18 @@ def frames_to_numpy(frames):
     """int32 CUDA/CPU tensor [..., 5] -> structured numpy records."""
     a = frames.detach().cpu().numpy()
     return np.ascontiguousarray(a).view(FRAME_DTYPE).reshape(a.shape[:-1])
+
+
+def check_not_truncated(states, max_frames):
+    """Raises if a stream stopped because its record buffer was full (done == 0 and nframes == max_frames,
+    include/fsk_b200.h): its decode is incomplete until the caller consumes the records, resets nframes and
+    calls rx_batch again.  Synchronises (reads the states back)."""
+    st = states_to_numpy(states)
+    bad = np.nonzero((st["done"] == 0) & (st["nframes"] >= int(max_frames)))[0]
+    if bad.size:
+        raise RuntimeError("rx_batch: %d stream(s) filled their %d-record buffer before the end of their samples "
+                           "(first: stream %d); use RxEngine.max_frames(nsamples) or resume them" % (
+                               bad.size, int(max_frames), int(bad[0])))
 
 
 def states_to_numpy(states):

@@ -17,7 +17,7 @@ mkdir -p "$ROOT/variants"
 RUN="$ROOT/variants/run.sh"
 cat > "$RUN" <<'EOS'
 #!/bin/bash
-one() { label=$1; lib=$2; shift 2; env FSK_B200_LIB=$lib "$@" timeout 300 python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu 2>/dev/null | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.readlines()[-1]); print('$label:', round(d['value']), 'Ms/s', round(d['roofline']['kernel_ms'],2), 'ms frac', round(d['roofline']['frac'],3))"; }
+one() { label=$1; lib=$2; shift 2; env FSK_B200_LIB=$lib "$@" timeout 300 python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu --no-configs 2>/dev/null | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.readlines()[-1]); print('$label:', round(d['value']), 'Ms/s', round(d['roofline']['kernel_ms'],2), 'ms frac', round(d['roofline']['frac'],3))"; }
 EOS
 for spec in "$@"; do
     name=${spec%%:*}; rest=${spec#*:}; flags=${rest%%:*}; envs=""
