@@ -699,6 +699,94 @@ __device__ __forceinline__ Found find_frame_fast_body(const Ring rg, unsigned po
     return best;
 }
 
+/* The fine search of the rx loop (src/minimodem.c:1357-1389: try_step = try_max/8, no limit) by SLIDING.
+ * Its candidates are `step` samples apart, a fraction of a bit window, so the window sums of a candidate
+ * are those of its neighbour minus the `step` samples that left each window plus the `step` that entered:
+ * 2*step multiply-adds per window instead of bit_nsamples.  For that the correlation phase must not
+ * restart with the candidate: the table is indexed by (candidate offset + sample) -- geom.tw_entries
+ * covers try_max + bit_nsamples + a step -- which changes every window sum by a unit phase factor only,
+ * i.e. not its magnitude (src/fsk.c:107-114 takes the magnitude).  The candidates are visited in
+ * ascending order instead of the zig-zag of src/fsk.c:477-484; among equal confidences the one the
+ * reference would have met first is kept, which is what its strict `best_c < c` does.  Works for any
+ * frame geometry (no tiling needed); fp32 error grows by a few 1e-7 of the window's terms per slide. */
+template <int G, int W, int L>
+__device__ __forceinline__ Found find_frame_slide(const Ring rg, unsigned pos_off,
+	const fsk_b200_geom &geo, const LaneWin<W> &lw, int sel, unsigned tw_s, unsigned g, unsigned gmask,
+	unsigned try_first, unsigned try_max, unsigned step, unsigned &ncand)
+{
+    const float *ring = static_cast<const float *>(__cvta_shared_to_generic(rg.ring_s));
+    const float4 *tw = static_cast<const float4 *>(__cvta_shared_to_generic(tw_s));
+    const unsigned N = geo.bit_nsamples, R = rg.R;
+    const unsigned part = g % L;
+    /* the set src/fsk.c:477-484 visits: first + k*step for -k_dn <= k <= k_up (the scan ends at the first
+     * upward step that reaches try_max, so it never gets further down than it got up) */
+    const unsigned k_up = (try_max - 1u - try_first) / step;
+    const unsigned k_dn = min(try_first / step, k_up);
+    unsigned t = try_first - k_dn * step;
+    const unsigned ncands = k_dn + k_up + 1u;
+
+    const float *p[W];
+    float acc[W][4];
+#pragma unroll
+    for (int j = 0; j < W; j++) {
+	p[j] = ring + ring_wrap(ring_wrap(pos_off + t, R) + lw.beg[j], R);
+	acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
+    }
+    corr_pass<0, W, W, L>(acc, p, tw + t, part, N);	/* the lowest candidate: a full correlation, phase index t + n */
+
+    Found best = { 0.f, 0.f, 0u, 0u, 0u };
+    unsigned best_order = 0;
+#pragma unroll 1
+    for (unsigned i = 0;; i++) {
+	ncand++;
+	float wsum[W][4];
+#pragma unroll
+	for (int j = 0; j < W; j++)
+#pragma unroll
+	    for (int k = 0; k < 4; k++)
+		wsum[j][k] = acc[j][k];			/* frame_finish may reduce in place */
+	unsigned lo, hi;
+	float a;
+	const float c = frame_finish<G, W, L, false, false>(wsum, p, lw.own, lw.exp, geo, tw, sel, g, gmask, lo, hi, a);
+	/* place in the reference's visiting order: first, +1, -1, +2, -2, ... */
+	const unsigned order = t >= try_first ? (t == try_first ? 0u : 2u * ((t - try_first) / step) - 1u)
+	    : 2u * ((try_first - t) / step);
+	if (best.confidence < c || (best.confidence == c && c > 0.f && order < best_order)) {
+	    best = Found{ c, a, t, lo, hi };
+	    best_order = order;
+	}
+	if (i + 1u == ncands)
+	    break;
+	/* slide every window from t to t + step */
+	const unsigned base = ring_wrap(pos_off + t, R);
+	const float *pr[W], *pa[W];
+#pragma unroll
+	for (int j = 0; j < W; j++) {
+	    const unsigned w0 = ring_wrap(base + lw.beg[j], R);
+	    pr[j] = ring + w0;					/* the samples that leave: [t, t + step) of the window */
+	    pa[j] = ring + ring_wrap(w0 + N, R);		/* the samples that enter: [t + N, t + N + step) */
+	}
+	const float4 *twr = tw + t, *twa = tw + t + N;
+#pragma unroll 2
+	for (unsigned n = part; n < step; n += L) {
+	    const float4 cr = twr[n], ca = twa[n];
+#pragma unroll
+	    for (int j = 0; j < W; j++) {
+		const float xr = pr[j][n], xa = pa[j][n];
+		acc[j][0] = fmaf(xa, ca.x, fmaf(-xr, cr.x, acc[j][0]));
+		acc[j][1] = fmaf(xa, ca.y, fmaf(-xr, cr.y, acc[j][1]));
+		acc[j][2] = fmaf(xa, ca.z, fmaf(-xr, cr.z, acc[j][2]));
+		acc[j][3] = fmaf(xa, ca.w, fmaf(-xr, cr.w, acc[j][3]));
+	    }
+	}
+	t += step;
+#pragma unroll
+	for (int j = 0; j < W; j++)
+	    p[j] = ring + ring_wrap(ring_wrap(pos_off + t, R) + lw.beg[j], R);	/* window starts (fp64 re-sum) */
+    }
+    return best;
+}
+
 /* the same, as a call: the kernels with more than one search site keep one copy of the code */
 template <int G, int W, int L>
 __device__ __noinline__ Found find_frame_fast(const Ring rg, unsigned pos_off,

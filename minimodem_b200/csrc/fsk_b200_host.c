@@ -220,6 +220,7 @@ int fsk_b200_geom_from(unsigned int frame_nsamples, const char *expect_data,
     g->eps_unscaled = 1.1920928955078125e-07f / g->mag_scalar;
     g->inv_n_bits = 1.0f / (float)(int)g->n_bits;
     g->lanes_per_window = 1;
+    g->tw_entries = g->bit_nsamples;
     for (int k = 0; k < 2; k++) {
 	const char *e = k ? (expect_sync ? expect_sync : expect_data) : expect_data;
 	for (unsigned int b = 0; b < g->n_bits; b++) {
@@ -552,9 +553,18 @@ fsk_b200_engine *fsk_b200_engine_new(const fsk_b200_rx_params *params)
     e->loopc.try_max_carrier = params->try_max_carrier;
     e->loopc.confidence_threshold = params->confidence_threshold;
     e->loopc.confidence_search_limit = params->confidence_search_limit;
+    {	/* the sliding fine search indexes the table by (candidate offset + sample): up to try_max + N + a step */
+	const unsigned tmax = params->try_max_nocarrier > params->try_max_carrier
+	    ? params->try_max_nocarrier : params->try_max_carrier;
+	const unsigned want = e->geom.bit_nsamples + 2u * tmax;
+	if ((size_t)want * 16u <= 12u * 1024u && !getenv("FSK_B200_NO_SLIDE")) {
+	    e->geom.tw_entries = want;
+	    e->loopc.slide = 1;
+	}
+    }
     e->ce = fsk_b200_cuda_engine_new();
     if (!e->ce || fsk_b200_cuda_set_table(e->ce, params->fftsize, params->b_mark,
-		params->b_space, e->geom.bit_nsamples) != 0) {
+		params->b_space, e->geom.tw_entries) != 0) {
 	if (e->ce)
 	    fsk_b200_cuda_engine_destroy(e->ce);
 	free(e);

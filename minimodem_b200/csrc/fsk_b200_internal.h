@@ -22,6 +22,8 @@ typedef struct fsk_b200_geom {
     float	mag_scalar;		/* 2.0f / bit_nsamples, src/fsk.c:132 */
     float	eps_unscaled;		/* FLT_EPSILON / mag_scalar: the :279 threshold before scaling */
     float	inv_n_bits;		/* 1.0f / n_bits */
+    unsigned int tw_entries;		/* twiddle table entries the kernels stage in shared memory: bit_nsamples, or
+					 * bit_nsamples + 2 * try_max for the sliding fine search (absolute phase index) */
     float	rot[4];			/* exp(-2 pi i b N / fftsize) for b = b_mark, b_space as (re, im), N = bit_nsamples:
 					 * the phase step from one bit period to the next (shared-segment search) */
     unsigned int bit_begin[FSK_B200_MAX_BITS];
@@ -34,6 +36,7 @@ typedef struct fsk_b200_loopc {
     unsigned int frame_nsamples, expect_nsamples, nsamples_overscan;
     unsigned int try_max_nocarrier, try_max_carrier;
     float	confidence_threshold, confidence_search_limit;
+    unsigned int slide;			/* 1: the per-candidate rx kernel runs its fine searches by sliding (geom.tw_entries covers it) */
 } fsk_b200_loopc;
 
 /* ---- shared-segment search plan (the "multi" rx kernel) --------------------------------------

@@ -72,7 +72,7 @@ template <int G>
 __device__ __forceinline__ Smem carve(float4 *smem, const fsk_b200_geom &geo,
 	const float4 *__restrict__ tw_global, unsigned tw_in_smem, unsigned ring_floats)
 {
-    const unsigned N = geo.bit_nsamples, wpb = blockDim.x >> 5;
+    const unsigned N = geo.tw_entries, wpb = blockDim.x >> 5;	/* table entries staged (>= bit_nsamples) */
     Smem s;
     float4 *p = smem;
     if (tw_in_smem) {
@@ -481,7 +481,11 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
 			    if (pass == 0 && !skip)
 				mhint = r.ncand > 1u;
 			}
-		    } else
+		    } else if (MODE == 0 && FILL != 3 && pass == 1 && lc.slide)
+			/* :1373, the fine search: its candidates in ascending order, each from the one before */
+			f = find_frame_slide<G, W, L>(rg, pos_off, geo, lw, which, tw_s, g, gmask, try_first, try_max,
+				step, ncand);
+		    else
 			f = find_frame_fast_body<G, W, L>(rg, pos_off, geo, lw, which, tw_s, g,
 				gmask, try_first, try_max, step, limit, ready, pending, ncand);
 		    if (pass) {
@@ -1310,6 +1314,7 @@ struct Shape {
     size_t smem;
     fsk_b200_geom geo;
     fsk_b200_mplan mplan;	/* mode 2 */
+    unsigned slide;		/* mode 0: fine searches by sliding (extended twiddle table staged) */
 };
 
 /* (G, W, L) combinations that are instantiated for the fast path: G lanes per
@@ -1390,7 +1395,7 @@ static int pick_shape(const CudaEngine *ce, const fsk_b200_geom *g, unsigned nee
     sh->geo = *g;
     memset(&sh->mplan, 0, sizeof(sh->mplan));
     const size_t smem_max = (size_t)ce->smem_optin;
-    const size_t tw_bytes = (size_t)g->bit_nsamples * sizeof(float4);
+    const size_t tw_bytes = (size_t)g->bit_nsamples * sizeof(float4);	/* the sliding search's extension is added at the end */
     sh->tw_in_smem = tw_bytes <= 24 * 1024;
     const size_t fixed = sh->tw_in_smem ? tw_bytes : 0;
     const size_t pad_bytes = (size_t)((g->bit_nsamples + 3u) & ~3u) * 4;
@@ -1479,6 +1484,18 @@ static int pick_shape(const CudaEngine *ce, const fsk_b200_geom *g, unsigned nee
 	    L = L2;
 	}
     }
+    /* the table as staged: the window-relative entries, or (per-candidate kernel with the sliding fine
+     * search) the absolute-index extension the host layer prepared, if it still fits */
+    sh->geo.tw_entries = g->bit_nsamples;
+    sh->slide = 0;
+    if (sh->mode == 0 && lc && lc->slide && g->tw_entries > g->bit_nsamples && sh->tw_in_smem) {
+	const size_t extra = (size_t)(g->tw_entries - g->bit_nsamples) * sizeof(float4);
+	if (sh->smem + extra <= smem_max) {
+	    sh->smem += extra;
+	    sh->geo.tw_entries = g->tw_entries;
+	    sh->slide = 1;
+	}
+    }
     sh->G = G;
     sh->W = W;
     sh->L = L;
@@ -1519,7 +1536,7 @@ extern "C" int fsk_b200_cuda_find_frame_batch(void *p, const fsk_b200_geom *g, c
 	const float *limit, const uint8_t *expect_sel, fsk_b200_frame *frames, float *bit_mags, void *stream)
 {
     CudaEngine *ce = (CudaEngine *)p;
-    if (!ce->d_tw || ce->tw_n < g->bit_nsamples) {
+    if (!ce->d_tw || ce->tw_n < g->tw_entries) {
 	fsk_b200_set_error("find_frame_batch: twiddle table not set");
 	return -EINVAL;
     }
@@ -1582,7 +1599,7 @@ static int rx_batch_any(CudaEngine *ce, const fsk_b200_geom *g, const fsk_b200_l
 	uint32_t nsamples_all, fsk_b200_frame *frames, uint32_t max_frames,
 	fsk_b200_stream_state *states, void *stream)
 {
-    if (!ce->d_tw || ce->tw_n < g->bit_nsamples) {
+    if (!ce->d_tw || ce->tw_n < g->tw_entries) {
 	fsk_b200_set_error("rx_batch: twiddle table not set");
 	return -EINVAL;
     }
@@ -1593,6 +1610,9 @@ static int rx_batch_any(CudaEngine *ce, const fsk_b200_geom *g, const fsk_b200_l
 	? lc->try_max_nocarrier : lc->try_max_carrier;
     const unsigned max_advance = tmax - 1u + lc->frame_nsamples;	/* :1407, overscan >= 0 */
     pick_shape(ce, g, tmax - 1u + g->span, max_advance, nstreams, &sh, lc);
+    fsk_b200_loopc lc_launch = *lc;
+    lc_launch.slide = sh.slide;
+    lc = &lc_launch;
     const RxArgs a = { elem == 4 ? (const float *)samples : NULL, elem == 2 ? (const int16_t *)samples : NULL,
 	(unsigned)nstreams, stride, nsamples, nsamples_all, frames, max_frames, states };
     cudaStream_t st = (cudaStream_t)stream;
@@ -1644,7 +1664,8 @@ static int rx_batch_any(CudaEngine *ce, const fsk_b200_geom *g, const fsk_b200_l
     snprintf(ce->last_kernel, sizeof(ce->last_kernel),
 	    "k_rx<G=%d,W=%d,L=%d,mode=%d(%s),fill=%d,src=%s> threads=%d ring=%u smem=%zu blocks=%d", sh.G, sh.W, sh.L,
 	    sh.mode, sh.mode == 2 ? "shared-segment" : sh.mode == 0 ? "per-candidate" : "generic",
-	    sh.mode == 0 ? ce->fill : 0, elem == 2 ? "s16" : "f32", sh.wpb * 32, sh.ring, sh.smem, sh.blocks);
+	    sh.mode == 0 ? ce->fill : 0, elem == 2 ? (sh.slide ? "s16,slide" : "s16") : (sh.slide ? "f32,slide" : "f32"),
+	    sh.wpb * 32, sh.ring, sh.smem, sh.blocks);
     if (e != cudaSuccess) {
 	fsk_b200_set_error("rx_batch launch (G=%d W=%d L=%d mode=%d ring=%u smem=%zu): %s", sh.G, sh.W,
 		sh.L, sh.mode, sh.ring, sh.smem, cudaGetErrorString(e));
