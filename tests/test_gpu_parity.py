@@ -669,6 +669,17 @@ def test_decode_batch_every_decoder(kind):
         assert bytes(o[s, :c[s]]) == want, (kind, s)
         total += len(want)
     assert total > 1000
+    # independent of this repository's decoder source: the UNMODIFIED reference decoders (oracle/_ref/libfsk_ref.so,
+    # src/databits_*.c, src/uic_codes.c) on the same records, for the decoders that keep no state between calls
+    if orc.have_ref() and kind in ("ascii8", "binary", "uic-ground", "uic-train"):
+        for s in range(0, nstreams, 5):
+            frames = []
+            for r in rec[s, :nfr[s]]:
+                if int(r[4]) == orc.FRAME_REPORT:
+                    continue
+                frames.append((int(r[0]) | (int(r[1]) << 32), 0.0, 0.0, int(r[4]) & 0x7FFFFFFF,
+                               1 if int(r[4]) & orc.FRAME_ACQUIRED else 0, 0))
+            assert bytes(o[s, :c[s]]) == orc.ref_decode(rx, frames, decoder=kind), (kind, s, "vs the reference decoder")
 
     # the same streams in two batches with the decoder state carried on the device
     half = max_frames // 2
