@@ -479,6 +479,7 @@ def run_ours(a):
     roofline = {"bound": "hbm", "achieved": head["achieved_gbs"], "peak": peak, "unit": "GB/s",
                 "frac": head["roofline_frac"], "traffic": measured_traffic(a.mode, a.rate, S, n),
                 "algorithmic_bytes": S * n * bytes_per_sample, "peak_source": peak_src, "kernel": "k_rx",
+                "kernel_variant": eng.last_kernel(),
                 "kernel_ms": ms_kernel, "algorithmic_bytes_per_sample": bytes_per_sample,
                 "kernel_source_sha16": kernel_source_hash(),
                 "candidates_per_frame": head["candidates_per_frame"],
@@ -593,7 +594,7 @@ def run_ours(a):
                 ms_s, ms_k, _ = time_rx(torch, dist, world, dev, ceng, cx, cn, cmax, cfr, cst, a.config_steps, 3)
                 r = summarize(mm, torch, dist, world, dev, cwl, cfr, cst, ms_s, ms_k,
                               clean=not (awgn or offset), peak=peak)
-                r.update({"key": "%s_%s" % (key, suffix),
+                r.update({"key": "%s_%s" % (key, suffix), "kernel": ceng.last_kernel(),
                           "workload": workload_name(mode, rate, cS, cn, ", amplitude %.2f%s%s" % (
                               amp, ", AWGN sigma %.2f" % awgn if awgn else "",
                               ", constant offset -%.2f (the reference's --Xrxnoise)" % offset if offset else "")),

@@ -1079,6 +1079,281 @@ __device__ __forceinline__ FoundN find_frame_multi(const Ring rg, unsigned pos_o
     }
     return FoundN{ best, ncand };
 }
+/* ======================================================================== */
+/* PREFIX: chunk-prefix table search (plan: fsk_b200_internal.h, fsk_b200_pfx) */
+/* ======================================================================== */
+/* One stream per warp.  pfx_build demodulates the search span once per rx-loop iteration; every
+ * candidate of the coarse and of the fine search of that iteration is then analysed from the table
+ * (pfx_search): a candidate costs a few loads per bit window, independent of bit_nsamples, and
+ * 32 / bs candidates are analysed side by side, one lane per window boundary. */
+
+/* what a lane needs to know about its place in a candidate slot, computed once per kernel */
+struct PfxLane {
+    unsigned cslot;	/* candidate slot of this lane (>= 32 / bs never: bs divides 32) */
+    unsigned kk;	/* boundary index inside the slot */
+    unsigned bb;	/* offset of this lane's boundary inside a candidate (0 for an idle lane) */
+    unsigned peer;	/* lane that holds the END boundary of this lane's window */
+    unsigned exp;	/* expect value (0, 1, 2) of this lane's window: bits 0-1 data string, bits 2-3 sync string */
+    unsigned idx0;	/* rotation-table index of the first chunk of this lane's run (table build) */
+    bool win;		/* this lane decides a bit window (kk < n_bits) */
+};
+
+__device__ __forceinline__ PfxLane pfx_lane(const fsk_b200_geom &geo, const fsk_b200_pfx &pg, unsigned lane)
+{
+    PfxLane pl;
+    const unsigned nb = geo.n_bits, N = geo.bit_nsamples;
+    pl.cslot = lane / pg.bs;
+    pl.kk = lane % pg.bs;
+    pl.win = pl.kk < nb;
+    if (pl.win)
+	pl.bb = geo.bit_begin[pl.kk];
+    else if (pg.tiles)
+	pl.bb = pl.kk == nb ? geo.bit_begin[nb - 1u] + N : 0u;
+    else
+	pl.bb = pl.kk < 2u * nb ? geo.bit_begin[pl.kk - nb] + N : 0u;
+    pl.peer = (lane + (pg.tiles ? 1u : nb)) & 31u;
+    const unsigned e0 = pl.win ? geo.expect[0][pl.kk] : 2u, e1 = pl.win ? geo.expect[1][pl.kk] : 2u;
+    pl.exp = e0 | (e1 << 2);
+    pl.idx0 = (pg.s4 * lane * pg.cpl) % pg.fp;
+    return pl;
+}
+
+/* a chunk's four samples against both tones, phase counted from the chunk's first sample:
+ * (re, im) mark, (re, im) space.  loc[j-1] = exp(-2 pi i b j / fftsize), j = 1..3 */
+__device__ __forceinline__ float4 pfx_local(float x0, float x1, float x2, float x3, const float (&loc)[3][4])
+{
+    float4 s;
+    s.x = fmaf(x3, loc[2][0], fmaf(x2, loc[1][0], fmaf(x1, loc[0][0], x0)));
+    s.y = fmaf(x3, loc[2][1], fmaf(x2, loc[1][1], x1 * loc[0][1]));
+    s.z = fmaf(x3, loc[2][2], fmaf(x2, loc[1][2], fmaf(x1, loc[0][2], x0)));
+    s.w = fmaf(x3, loc[2][3], fmaf(x2, loc[1][3], x1 * loc[0][3]));
+    return s;
+}
+/* acc += rot * s, tone by tone (complex) */
+__device__ __forceinline__ void pfx_rot_acc(float4 &acc, const float4 rt, const float4 s)
+{
+    acc.x = fmaf(-rt.y, s.y, fmaf(rt.x, s.x, acc.x));
+    acc.y = fmaf(rt.y, s.x, fmaf(rt.x, s.y, acc.y));
+    acc.z = fmaf(-rt.w, s.w, fmaf(rt.z, s.z, acc.z));
+    acc.w = fmaf(rt.w, s.z, fmaf(rt.z, s.w, acc.w));
+}
+
+/* The table of one search span: chunk m = ring floats [base + 4m, base + 4m + 4) (base = ring offset of the
+ * 16-byte chunk that holds the search position).  Lane g walks the chunks [g * cpl, (g + 1) * cpl) in
+ * order, stores the sum of its EARLIER chunks in pre[m] and its total in tot[g]. */
+__device__ __forceinline__ void pfx_build(const float *ring, unsigned R, unsigned base, unsigned nchunks,
+	float4 *pre, float4 *tot, const float4 *twc, const fsk_b200_pfx &pg, const PfxLane &pl, unsigned lane)
+{
+    const unsigned m0 = lane * pg.cpl;
+    const unsigned m1 = min(m0 + pg.cpl, nchunks);
+    unsigned off = base + 4u * m0;
+    if (off >= R)
+	off -= R;
+    unsigned idx = pl.idx0;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 2
+    for (unsigned m = m0; m < m1; m++) {
+	const float4 x = *reinterpret_cast<const float4 *>(ring + off);
+	const float4 rt = twc[idx];
+	pre[m] = acc;
+	pfx_rot_acc(acc, rt, pfx_local(x.x, x.y, x.z, x.w, pg.loc));
+	off += 4u;
+	if (off == R)
+	    off = 0u;
+	idx += pg.s4;
+	if (idx >= pg.fp)
+	    idx -= pg.fp;
+    }
+    tot[lane] = acc;
+}
+
+/* One round: the candidates `t` of the 32 / bs slots (valid or not, per slot), every window of every one
+ * of them from the table.  All 32 lanes take part (full-mask shuffles).  Returns this slot's
+ * confidence (0 for an invalid slot or a rejected candidate); all lanes of a slot hold the same values. */
+__device__ __forceinline__ float pfx_round(const float *ring, unsigned R, unsigned base, unsigned r0, unsigned t,
+	bool valid, const float4 *pre, const float4 *tot, const float4 *twc, const float4 *__restrict__ tw_sample,
+	const fsk_b200_pfx &pg, const fsk_b200_geom &geo, const PfxLane &pl, int sel,
+	unsigned &bits_lo_out, unsigned &bits_hi_out, float &ampl_out, float2 *bit_mags = nullptr)
+{
+    const unsigned FULL = 0xffffffffu;
+    const unsigned N = geo.bit_nsamples, nb = geo.n_bits;
+    /* this lane's boundary: sample i of the span, r samples into chunk m */
+    const unsigned i = r0 + (valid ? t : 0u) + pl.bb;
+    const unsigned m = i >> 2, r = i & 3u;
+    unsigned off = base + (i & ~3u);
+    if (off >= R)
+	off -= R;
+    const float4 x = *reinterpret_cast<const float4 *>(ring + off);
+    const unsigned sm = pg.s4 * m;
+    const unsigned idx = sm - (unsigned)(((float)sm + 0.5f) * pg.inv_fp) * pg.fp;
+    const float4 rt = twc[idx];
+    float4 P = pre[m];
+    const unsigned l_b = (unsigned)(((float)m + 0.5f) * pg.inv_cpl);
+    /* the r samples of the boundary's own chunk that precede it (a chunk past the requested samples is
+     * only ever met with r == 0: nothing of it is used) */
+    pfx_rot_acc(P, rt, pfx_local(r > 0u ? x.x : 0.f, r > 1u ? x.y : 0.f, r > 2u ? x.z : 0.f, 0.f, pg.loc));
+    /* the end of this lane's window is another lane's boundary */
+    float4 S;
+    S.x = __shfl_sync(FULL, P.x, pl.peer) - P.x;
+    S.y = __shfl_sync(FULL, P.y, pl.peer) - P.y;
+    S.z = __shfl_sync(FULL, P.z, pl.peer) - P.z;
+    S.w = __shfl_sync(FULL, P.w, pl.peer) - P.w;
+    const unsigned l_e = __shfl_sync(FULL, l_b, pl.peer);
+    const bool own = pl.win && valid;
+    if (own) {
+	for (unsigned l = l_b; l < l_e; l++) {		/* the lane-runs the window crosses */
+	    const float4 tl = tot[l];
+	    S.x += tl.x; S.y += tl.y; S.z += tl.z; S.w += tl.w;
+	}
+    }
+    /* per-window decision (src/fsk.c:158-169) and this lane's share of the sums (:271-289); magnitudes stay
+     * unscaled as in frame_finish */
+    const float eps_u = geo.eps_unscaled;
+    float tn = 0.f, am = 0.f, as = 0.f, sig = 0.f;
+    unsigned nm = 0, blo = 0, bhi = 0;
+    bool one = false;
+    if (own) {
+	float mag_mark = fast_sqrt(S.x * S.x + S.y * S.y);
+	float mag_space = fast_sqrt(S.z * S.z + S.w * S.w);
+	const float mag_hi = fmaxf(mag_mark, mag_space);
+	if (mag_hi != 0.f && fminf(mag_mark, mag_space) < eps_u + 2e-6f * mag_hi) {
+	    /* too close to the :279 threshold for fp32 sums (see needs_resum): the window again, in fp64, phase
+	     * counted from its first sample (the per-sample table, from global memory: rare) */
+	    double drm = 0., dim = 0., drs = 0., dis = 0.;
+	    unsigned q = base + i;
+	    if (q >= R)
+		q -= R;
+#pragma unroll 1
+	    for (unsigned n = 0; n < N; n++) {
+		const double xs = (double)ring[q];
+		const float4 c = __ldg(tw_sample + n);
+		drm = fma(xs, (double)c.x, drm);
+		dim = fma(xs, (double)c.y, dim);
+		drs = fma(xs, (double)c.z, drs);
+		dis = fma(xs, (double)c.w, dis);
+		if (++q == R)
+		    q = 0u;
+	    }
+	    const float frm = (float)drm, fim = (float)dim, frs = (float)drs, fis = (float)dis;
+	    mag_mark = sqrtf(frm * frm + fim * fim);
+	    mag_space = sqrtf(frs * frs + fis * fis);
+	}
+	one = mag_mark > mag_space;				/* strict: tie -> space */
+	sig = one ? mag_mark : mag_space;
+	const float noise = one ? mag_space : mag_mark;
+	const unsigned e = (pl.exp >> (sel ? 2 : 0)) & 3u;
+	if (bit_mags)
+	    bit_mags[pl.kk] = make_float2(sig * geo.mag_scalar, noise * geo.mag_scalar);
+	if (noise > eps_u)					/* :279 */
+	    tn = noise;
+	if (e != 2u && e != (one ? 1u : 0u))			/* pass 1, :211: poisons the noise sum */
+	    tn = INFINITY;
+	if (one) {
+	    am = sig;
+	    nm = 1u;
+	    if (pl.kk < 32u) blo = 1u << pl.kk; else bhi = 1u << (pl.kk - 32u);
+	} else
+	    as = sig;
+    }
+    /* the frame sums over the lanes of the slot (src/fsk.c:271-289) */
+    for (unsigned o = pg.bs >> 1; o; o >>= 1) {
+	tn += __shfl_xor_sync(FULL, tn, o);
+	am += __shfl_xor_sync(FULL, am, o);
+	as += __shfl_xor_sync(FULL, as, o);
+	nm += __shfl_xor_sync(FULL, nm, o);
+	blo |= __shfl_xor_sync(FULL, blo, o);
+    }
+    if (nb > 32u)
+	for (unsigned o = pg.bs >> 1; o; o >>= 1)
+	    bhi |= __shfl_xor_sync(FULL, bhi, o);
+    const float ts = am + as;
+    const unsigned n_space = nb - nm;
+    const float snr = fast_div(ts, tn);					/* :292, may be +inf */
+    const float avg_bit_sig = ts * geo.inv_n_bits * geo.mag_scalar;	/* :295, with the 2/N of :132 */
+    if (nm)
+	am = fast_div(am, (float)nm);					/* :298-301 */
+    if (n_space)
+	as = fast_div(as, (float)n_space);
+    float dv = 0.f;							/* :305-311 */
+    if (own) {
+	const float other = one ? am : as;
+	dv = fast_div(fabsf(sig - other), other);
+    }
+    for (unsigned o = pg.bs >> 1; o; o >>= 1)
+	dv += __shfl_xor_sync(FULL, dv, o);
+    const float divergence = dv * 2.f * geo.inv_n_bits;		/* :312-313 */
+    if (!valid || tn == INFINITY) {					/* pass 1 reject, :211-212 */
+	bits_lo_out = bits_hi_out = 0u;
+	ampl_out = 0.f;
+	return 0.f;
+    }
+    bits_lo_out = blo;
+    bits_hi_out = bhi;
+    ampl_out = avg_bit_sig;						/* :342 */
+    return snr * (1.0f - divergence);					/* :336 */
+}
+
+/* fsk_find_frame (src/fsk.c:449-538) over the table: the candidates in the reference's visiting order
+ * (first, +1, -1, +2, -2, ... steps; the scan ends at the first upward step that reaches try_max, and
+ * downward steps below 0 are skipped), 32 / bs of them per round.  The reference returns the first
+ * candidate in that order whose confidence reaches `limit` (everything before it was below the limit, so
+ * it is also the best so far), else the largest confidence, the earliest among equals (:492 is strict). */
+__device__ __forceinline__ Found pfx_search(const float *ring, unsigned R, unsigned base, unsigned r0,
+	const float4 *pre, const float4 *tot, const float4 *twc, const float4 *__restrict__ tw_sample,
+	const fsk_b200_pfx &pg, const fsk_b200_geom &geo, const PfxLane &pl, int sel, unsigned try_first,
+	unsigned try_max, unsigned step, float limit, unsigned lane, unsigned &ncand)
+{
+    const unsigned FULL = 0xffffffffu;
+    const unsigned cpr = 32u / pg.bs;
+    const unsigned k_up = (try_max - 1u - try_first) / step;
+    const unsigned k_dn = min(try_first / step, k_up);
+    const unsigned ncands = 1u + k_up + k_dn;
+    Found best = { 0.f, 0.f, 0u, 0u, 0u };
+#pragma unroll 1
+    for (unsigned o0 = 0; o0 < ncands; o0 += cpr) {
+	const unsigned o = o0 + pl.cslot;
+	const bool valid = o < ncands;
+	/* the o-th candidate of the visiting order */
+	unsigned t = try_first;
+	if (o > 2u * k_dn)
+	    t = try_first + (o - k_dn) * step;
+	else if (o & 1u)
+	    t = try_first + ((o + 1u) >> 1) * step;
+	else
+	    t = try_first - (o >> 1) * step;
+	unsigned lo, hi;
+	float a;
+	float c = pfx_round(ring, R, base, r0, t, valid, pre, tot, twc, tw_sample, pg, geo, pl, sel, lo, hi, a);
+	if (!(c > 0.f))
+	    c = 0.f;					/* NaN and negatives never win (:492) */
+	ncand += min(cpr, ncands - o0);
+	/* the round's winner: the earliest slot that reaches the limit, else the largest confidence
+	 * (the earliest among equals); slots are in visiting order */
+	const unsigned reach = __ballot_sync(FULL, c >= limit);
+	unsigned src;
+	if (reach)
+	    src = (unsigned)__ffs((int)reach) - 1u;
+	else {
+	    float cm = c;
+	    for (unsigned d = pg.bs; d < 32u; d <<= 1)
+		cm = fmaxf(cm, __shfl_xor_sync(FULL, cm, d));
+	    src = (unsigned)__ffs((int)__ballot_sync(FULL, c == cm)) - 1u;
+	}
+	const float cw = __shfl_sync(FULL, c, src);
+	const float aw = __shfl_sync(FULL, a, src);
+	const unsigned tw_ = __shfl_sync(FULL, t, src);
+	const unsigned low = __shfl_sync(FULL, lo, src);
+	const unsigned hiw = __shfl_sync(FULL, hi, src);
+	if (best.confidence < cw) {
+	    best = Found{ cw, aw, tw_, low, hiw };
+	    if (cw >= limit)
+		break;					/* :499 */
+	}
+    }
+    (void)lane;
+    return best;
+}
+
 /* ------------------------------------------------------------------------ */
 /* asynchronous ring fill: HBM -> shared memory, 16 bytes per cp.async,     */
 /* every sample fetched once; bytes at or past the valid length arrive as 0 */

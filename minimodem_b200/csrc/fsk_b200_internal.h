@@ -75,6 +75,28 @@ typedef struct fsk_b200_mplan {
 int fsk_b200_mplan_build(const fsk_b200_geom *g, const struct fsk_b200_loopc *lc, unsigned int slots,
 	fsk_b200_mplan *out);
 
+
+/* ---- chunk-prefix table search (the "prefix" rx kernel, k_rx MODE 3) ------------------------------
+ * Once per rx-loop iteration the 32 lanes of a stream's warp demodulate the whole search span
+ * (try_max - 1 + span samples) against both tones in 4-sample chunks -- every sample is multiplied once,
+ * whatever the number of candidates the coarse and the fine search then visit -- and leave, per chunk,
+ * the running sums of the lane's run of chunks (exclusive prefix) plus one total per lane-run.  A bit
+ * window of ANY candidate is then the difference of two boundary values (prefix + at most three samples
+ * of the boundary's own chunk) plus the totals of the runs in between: a handful of loads instead of
+ * bit_nsamples multiply-adds.  The phase is absolute (counted from the chunk that holds the search
+ * position), which changes a window's sums by a unit factor only (src/fsk.c:107-114 takes the magnitude). */
+typedef struct fsk_b200_pfx {
+    uint32_t	nbnd;		/* boundaries per candidate: n_bits + 1 when the windows tile, else 2 * n_bits (begin, end) */
+    uint32_t	bs;		/* lanes per candidate slot: the power of two >= nbnd; 32 / bs candidates are analysed side by side */
+    uint32_t	tiles;		/* 1: window w ends where window w + 1 begins */
+    uint32_t	cpl;		/* chunks per lane-run of the table build: ceil(nchunks / 32) */
+    float	inv_cpl;
+    uint32_t	fp, s4;		/* chunk m is rotated by table entry (s4 * m) mod fp: fp = fftsize / gcd(4, fftsize), s4 = 4 / gcd */
+    float	inv_fp;
+    uint32_t	nchunks;	/* table capacity per stream: (3 + try_max - 1 + span) / 4 + 1 for the widest search */
+    float	loc[3][4];	/* exp(-2 pi i b j / fftsize), j = 1..3, as (re, im) for b_mark, b_space: the samples of a chunk */
+} fsk_b200_pfx;
+
 void fsk_b200_set_error(const char *fmt, ...);
 
 /* host-side pure derivations (fsk_b200_host.c) */

@@ -66,11 +66,15 @@ struct Smem {
     float *ring;
     float2 *scr;
     unsigned long long *bars;	/* two mbarriers per stream (bulk fill) */
+    float4 *pre, *tot;		/* MODE 3: the stream's chunk-prefix table and its 32 lane-run totals */
 };
 
+/* pad: floats of the ring's head mirrored behind its end (0: no mirror); pfx_chunks: MODE 3 table entries
+ * per stream (0: none) */
 template <int G>
 __device__ __forceinline__ Smem carve(float4 *smem, const fsk_b200_geom &geo,
-	const float4 *__restrict__ tw_global, unsigned tw_in_smem, unsigned ring_floats)
+	const float4 *__restrict__ tw_global, unsigned tw_in_smem, unsigned ring_floats, unsigned pad,
+	unsigned pfx_chunks = 0)
 {
     const unsigned N = geo.tw_entries, wpb = blockDim.x >> 5;	/* table entries staged (>= bit_nsamples) */
     Smem s;
@@ -86,11 +90,17 @@ __device__ __forceinline__ Smem carve(float4 *smem, const fsk_b200_geom &geo,
     const unsigned spw = 32 / G;
     const unsigned slot = (threadIdx.x >> 5) * spw + (threadIdx.x & 31) / G;
     float *rings = reinterpret_cast<float *>(p);
-    const unsigned pad = ring_floats ? ((geo.bit_nsamples + 3u) & ~3u) : 0u;
+    if (!ring_floats)
+	pad = 0u;
     s.ring = rings + (size_t)slot * (ring_floats + pad);
     float2 *scrs = reinterpret_cast<float2 *>(rings + (size_t)wpb * spw * (ring_floats + pad));
     s.scr = scrs + (size_t)slot * geo.n_bits;
-    s.bars = reinterpret_cast<unsigned long long *>(scrs + (size_t)wpb * spw * geo.n_bits) + 2 * slot;
+    /* (an even number of float2 in all, so that what follows stays 16-byte aligned) */
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(scrs + (((size_t)wpb * spw * geo.n_bits + 1u) & ~(size_t)1u));
+    s.bars = bars + 2 * slot;
+    float4 *pfx = reinterpret_cast<float4 *>(bars + 2 * (size_t)wpb * spw);
+    s.pre = pfx + (size_t)slot * (pfx_chunks + 32u);
+    s.tot = s.pre + pfx_chunks;
     __syncthreads();
     return s;
 }
@@ -136,7 +146,7 @@ k_find_frame(const __grid_constant__ fsk_b200_geom geo, const float4 *__restrict
 	unsigned tw_in_smem, unsigned ring_floats, const __grid_constant__ FindArgs a)
 {
     FSK_DYN_SMEM(smem4);
-    const Smem sm = carve<G>(smem4, geo, tw_global, tw_in_smem, ring_floats);
+    const Smem sm = carve<G>(smem4, geo, tw_global, tw_in_smem, ring_floats, (geo.bit_nsamples + 3u) & ~3u);
     GROUP_VARS;
     const Ring rg = { smem_u32(sm.ring), ring_floats, (geo.bit_nsamples + 3u) & ~3u };
     const unsigned tw_s = tw_in_smem ? smem_u32(sm.tw) : 0u;	/* the fast path requires the table in shared memory */
@@ -220,22 +230,34 @@ k_find_frame(const __grid_constant__ fsk_b200_geom geo, const float4 *__restrict
 #ifndef FSK_MAXTHREADS
 #define FSK_MAXTHREADS 128
 #endif
+/* MODE 3 runs one stream per warp and shares one rotation table per block, so its blocks are large
+ * (up to 16 streams): 512 threads x 1 block caps it at 128 registers per thread */
+#ifndef FSK_PFX_MAXTHREADS
+#define FSK_PFX_MAXTHREADS 512
+#endif
 /* SRC 0: float32 rows; SRC 1: int16 PCM rows (N2, src/simpleaudio-sndfile.c:43-57), widened to the
  * reference's float = short / 32768 inside the ring fill: 2 bytes per sample of HBM traffic */
 template <int G, int W, int L, int MODE, int FILL, int SRC = 0>
-__global__ void __launch_bounds__(FSK_MAXTHREADS, (MODE == 2 && G >= 16) ? 3 : FSK_MINBLOCKS)
+__global__ void __launch_bounds__(MODE == 3 ? FSK_PFX_MAXTHREADS : FSK_MAXTHREADS,
+	MODE == 3 ? 1 : (MODE == 2 && G >= 16) ? 3 : FSK_MINBLOCKS)
 k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200_loopc lc,
 	const float4 *__restrict__ tw_global, unsigned tw_in_smem, unsigned ring_floats,
-	unsigned lookahead, const __grid_constant__ RxArgs a, const __grid_constant__ fsk_b200_mplan mp)
+	unsigned lookahead, const __grid_constant__ RxArgs a, const __grid_constant__ fsk_b200_mplan mp,
+	const float4 *__restrict__ tw_sample, const __grid_constant__ fsk_b200_pfx pg)
 {
     FSK_DYN_SMEM(smem4);
-    const Smem sm = carve<G>(smem4, geo, tw_global, tw_in_smem, ring_floats);
+    /* MODE 3 (chunk-prefix table): no window is ever walked linearly, so the ring has no mirror; the staged
+     * table (tw_global) is the chunk-rotation table, the per-sample one stays in global memory (tw_sample) */
+    const unsigned ring_pad = MODE == 3 ? 0u : (geo.bit_nsamples + 3u) & ~3u;
+    const Smem sm = carve<G>(smem4, geo, tw_global, tw_in_smem, ring_floats, ring_pad, MODE == 3 ? pg.nchunks : 0u);
     GROUP_VARS;
-    const Ring rg = { smem_u32(sm.ring), ring_floats, (geo.bit_nsamples + 3u) & ~3u };
+    const Ring rg = { smem_u32(sm.ring), ring_floats, ring_pad };
     const unsigned tw_s = tw_in_smem ? smem_u32(sm.tw) : 0u;	/* the fast path requires the table in shared memory */
     /* MODE 2 (shared-segment search) owns CONSECUTIVE bit periods per lane, MODE 0 interleaved windows */
     const LaneWin<W> lw = lane_windows<G, W, L>(geo, g);
     const LaneWinM<W> lwm = lane_windows_multi<G, W, L>(geo, g);
+    const PfxLane pfl = MODE == 3 ? pfx_lane(geo, pg, lane) : PfxLane();
+    const unsigned pre_s = smem_u32(sm.pre), tot_s = smem_u32(sm.tot);
     const unsigned R = ring_floats;
 
     for (unsigned s = (blockIdx.x * wpb + warp) * spw + sidx; s < a.nstreams;
@@ -447,7 +469,28 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
 		for (int pass = 0;; pass++) {
 		    nsearch++;
 		    Found f;
-		    if (MODE == 2) {
+		    if (MODE == 3) {
+			/* :1265, :1378 from the chunk-prefix table of this iteration's search span, built once
+			 * (before the coarse search) for both */
+			/* (shared-window addresses turned back into pointers here, so that the loads stay LDS/STS) */
+			const float *ringp = static_cast<const float *>(__cvta_shared_to_generic(rg.ring_s));
+			float4 *pre = static_cast<float4 *>(__cvta_shared_to_generic(pre_s));
+			float4 *tot = static_cast<float4 *>(__cvta_shared_to_generic(tot_s));
+			const float4 *twc = static_cast<const float4 *>(__cvta_shared_to_generic(tw_s));
+			const unsigned base = pos_off & ~3u;
+			if (pass == 0) {
+			    if (pending) {
+				cp_async_wait<0>();
+				__syncwarp(gmask);
+				pending = false;
+			    }
+			    pfx_build(ringp, R, base, ((pos_off & 3u) + try_max - 1u + geo.span) / 4u + 1u, pre, tot,
+				    twc, pg, pfl, lane);
+			    __syncwarp(gmask);
+			}
+			f = pfx_search(ringp, R, base, pos_off & 3u, pre, tot, twc, tw_sample, pg, geo, pfl, which,
+				try_first, try_max, step, limit, lane, ncand);
+		    } else if (MODE == 2) {
 			/* :1265, :1378 from shared segment sums.  Which plan: the window is the one chosen at the
 			 * top of the iteration (carrier then), coarse or fine.  A coarse search in the steady
 			 * state ends at its first candidate (:499), and one candidate alone is cheapest analysed
@@ -668,7 +711,7 @@ k_rx_ws(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b
 	const __grid_constant__ RxArgs a)
 {
     FSK_DYN_SMEM(smem4);
-    const Smem sm = carve<G>(smem4, geo, tw_global, 1u, ring_floats);
+    const Smem sm = carve<G>(smem4, geo, tw_global, 1u, ring_floats, (geo.bit_nsamples + 3u) & ~3u);
     GROUP_VARS;
     const Ring rg = { smem_u32(sm.ring), ring_floats, (geo.bit_nsamples + 3u) & ~3u };
     const unsigned tw_s = smem_u32(sm.tw);
@@ -1132,6 +1175,9 @@ struct CudaEngine {
     int lanes, wpb, ring, split, fill;
     char last_kernel[160];	/* what the latest rx / find_frame launch ran (diagnostics) */
     int multi;			/* 1 (default): shared-segment search where the mode allows it; 0: always per candidate */
+    int prefix;			/* chunk-prefix table search (mode 3): -1 (default) where it pays, 0 never, 1 wherever it fits */
+    float4 *d_twc;		/* mode 3: chunk-rotation table, twc_n = fftsize / gcd(4, fftsize) entries (0: not built) */
+    unsigned twc_n, twc_cap;
     /* single-stream staging */
     float *d_one;
     size_t d_one_cap;
@@ -1187,6 +1233,10 @@ extern "C" void *fsk_b200_cuda_engine_new(void)
      * single-candidate fast path; 2 everywhere it fits, always */
     ce->multi = -1;
     if ((e = getenv("FSK_B200_MULTI"))) ce->multi = atoi(e);
+    /* chunk-prefix table search: -1 (default) for bit periods of FSK_PREFIX_MIN_N samples and more, 0 never,
+     * 1 wherever the mode fits it */
+    ce->prefix = -1;
+    if ((e = getenv("FSK_B200_PREFIX"))) ce->prefix = atoi(e);
     /* 256 MiB of samples ON THE WIRE per slab, two slabs in flight: the float path runs at the PCIe
      * rate with that (54 GB/s).  The int16 path, measured with slabs of the same stream count (128 MiB
      * on the wire), reached 78 % of it -- about 0.7 ms per slab stayed exposed (one conversion plus
@@ -1216,6 +1266,7 @@ extern "C" void fsk_b200_cuda_engine_destroy(void *p)
     if (!ce)
 	return;
     cudaFree(ce->d_tw);
+    cudaFree(ce->d_twc);
     cudaFree(ce->d_one);
     cudaFree(ce->d_args);
     cudaFree(ce->d_frame);
@@ -1253,6 +1304,11 @@ extern "C" int fsk_b200_cuda_tune(void *p, int lanes, int wpb, int ring)
     ce->ring = ring;
     return 0;
 }
+
+#define FSK_PFX_MAX_TABLE_BYTES (16u * 1024u)
+#ifndef FSK_PREFIX_MIN_N
+#define FSK_PREFIX_MIN_N 170u	/* shortest bit period (samples) for which mode 3 is the default (measured: RTTY @8 kHz, 176) */
+#endif
 
 /* exp(-2 pi i k n / fftsize) for k = b_mark, b_space; the argument is reduced
  * exactly in integers and evaluated in double before rounding to float */
@@ -1304,6 +1360,48 @@ extern "C" int fsk_b200_cuda_set_table(void *p, int fftsize, unsigned b_mark, un
     ce->tw_fftsize = fftsize;
     ce->tw_bm = b_mark;
     ce->tw_bs = b_space;
+    /* mode 3: the phase of chunk m (4 samples) relative to chunk 0 is b * 4m / fftsize turns; 4m mod fftsize
+     * only takes multiples of gcd(4, fftsize), so the table has fftsize / gcd entries, entry e for the
+     * sample index e * gcd.  Kept only while it is small enough to be staged per block. */
+    ce->twc_n = 0;
+    {
+	const unsigned g4 = (fftsize % 4 == 0) ? 4u : (fftsize % 2 == 0) ? 2u : 1u;
+	const unsigned fp = (unsigned)fftsize / g4;
+	if ((size_t)fp * sizeof(float4) <= FSK_PFX_MAX_TABLE_BYTES) {
+	    float4 *hc = (float4 *)malloc(sizeof(float4) * fp);
+	    if (!hc)
+		return -ENOMEM;
+	    for (unsigned i = 0; i < fp; i++) {
+		const unsigned long long n = (unsigned long long)i * g4;
+		const double am = 2.0 * M_PI * (double)(((unsigned long long)b_mark * n) % F) / (double)F;
+		const double as = 2.0 * M_PI * (double)(((unsigned long long)b_space * n) % F) / (double)F;
+		hc[i].x = (float)cos(am);
+		hc[i].y = (float)-sin(am);
+		hc[i].z = (float)cos(as);
+		hc[i].w = (float)-sin(as);
+	    }
+	    if (ce->twc_cap < fp) {
+		cudaFree(ce->d_twc);
+		ce->d_twc = NULL;
+		ce->twc_cap = 0;
+		if (cudaMalloc(&ce->d_twc, sizeof(float4) * fp) != cudaSuccess) {
+		    (void)cudaGetLastError();
+		    free(hc);
+		    return 0;			/* mode 3 is simply not offered */
+		}
+		ce->twc_cap = fp;
+	    }
+	    cudaError_t err2 = cudaMemcpy(ce->d_twc, hc, sizeof(float4) * fp, cudaMemcpyHostToDevice);
+	    if (err2 == cudaSuccess)
+		err2 = cudaDeviceSynchronize();
+	    free(hc);
+	    if (err2 != cudaSuccess) {
+		fsk_b200_set_error("set_table: %s", cudaGetErrorString(err2));
+		return -EIO;
+	    }
+	    ce->twc_n = fp;
+	}
+    }
     return 0;
 }
 
@@ -1314,6 +1412,7 @@ struct Shape {
     size_t smem;
     fsk_b200_geom geo;
     fsk_b200_mplan mplan;	/* mode 2 */
+    fsk_b200_pfx pfx;		/* mode 3 */
     unsigned slide;		/* mode 0: fine searches by sliding (extended twiddle table staged) */
 };
 
@@ -1484,9 +1583,80 @@ static int pick_shape(const CudaEngine *ce, const fsk_b200_geom *g, unsigned nee
 	    L = L2;
 	}
     }
+    memset(&sh->pfx, 0, sizeof(sh->pfx));
+    if (lc && ce->prefix && ce->fill == 0 && ce->twc_n && ring_min >= 128u
+	    && (ce->prefix > 0 || g->bit_nsamples >= FSK_PREFIX_MIN_N)) {
+	/* the rx loop's searches from a chunk-prefix table (mode 3): one stream per warp, one lane per
+	 * window boundary of a candidate, the ring without its mirror plus the table per stream */
+	fsk_b200_pfx &pf = sh->pfx;
+	const unsigned nb = g->n_bits, N = g->bit_nsamples;
+	pf.tiles = 1;
+	for (unsigned w = 0; w + 1 < nb; w++)
+	    if (g->bit_begin[w + 1] != g->bit_begin[w] + N)
+		pf.tiles = 0;
+	pf.nbnd = pf.tiles ? nb + 1u : 2u * nb;
+	pf.bs = 1;
+	while (pf.bs < pf.nbnd)
+	    pf.bs <<= 1;
+	pf.nchunks = (3u + need_floats) / 4u + 1u;
+	/* odd: the 32 lanes of the table build walk their runs in step, cpl float4 apart, and only an odd stride
+	 * spreads a quarter-warp's 16-byte accesses over all banks */
+	pf.cpl = ((pf.nchunks + 31u) / 32u) | 1u;
+	pf.inv_cpl = 1.0f / (float)pf.cpl;
+	const unsigned F = (unsigned)ce->tw_fftsize;
+	const unsigned g4 = (F % 4u == 0) ? 4u : (F % 2u == 0) ? 2u : 1u;
+	pf.fp = F / g4;
+	pf.s4 = 4u / g4;
+	pf.inv_fp = 1.0f / (float)pf.fp;
+	for (unsigned j = 1; j <= 3; j++) {
+	    const double am = 2.0 * M_PI * (double)(((unsigned long long)ce->tw_bm * j) % F) / (double)F;
+	    const double as = 2.0 * M_PI * (double)(((unsigned long long)ce->tw_bs * j) % F) / (double)F;
+	    pf.loc[j - 1][0] = (float)cos(am);
+	    pf.loc[j - 1][1] = (float)-sin(am);
+	    pf.loc[j - 1][2] = (float)cos(as);
+	    pf.loc[j - 1][3] = (float)-sin(as);
+	}
+	const unsigned ring3 = ce->ring ? ring : ring_min;
+	const size_t table = (size_t)pf.fp * sizeof(float4);
+	const size_t per_stream = (size_t)ring3 * 4 + (size_t)nb * sizeof(float2) + 16 + ((size_t)pf.nchunks + 32u) * sizeof(float4);
+	/* warps (= streams) per block: the most resident streams per SM (each block pays the table and 1 KiB) */
+	const size_t sm_total = (size_t)ce->smem_optin + 1024;
+	int best_wpb = 0;
+	size_t best_streams = 0;
+	for (int w = 1; w <= FSK_PFX_MAXTHREADS / 32; w++) {
+	    const size_t blk = ((table + (size_t)w * per_stream + 16 + 15) & ~(size_t)15);
+	    if (blk > smem_max)
+		break;
+	    size_t nblk = sm_total / (blk + 1024);
+	    if (nblk > 32)
+		nblk = 32;
+	    size_t streams = nblk * (size_t)w;
+	    if (streams > 64)
+		streams = 64;
+	    if (streams > best_streams) {
+		best_streams = streams;
+		best_wpb = w;
+	    }
+	}
+	if (ce->wpb && ce->prefix > 0) {
+	    const size_t blk = ((table + (size_t)ce->wpb * per_stream + 16 + 15) & ~(size_t)15);
+	    if (blk <= smem_max)
+		best_wpb = ce->wpb;
+	}
+	if (pf.nbnd <= 32u && best_wpb > 0 && pf.nchunks < 16384u && g->bit_nsamples <= ring3) {
+	    sh->mode = 3;
+	    G = 32;
+	    W = 1;
+	    L = 1;
+	    wpb = best_wpb;
+	    ring = ring3;
+	    sh->tw_in_smem = 1;
+	    sh->smem = ((table + (size_t)wpb * per_stream + 16 + 15) & ~(size_t)15);
+	}
+    }
     /* the table as staged: the window-relative entries, or (per-candidate kernel with the sliding fine
      * search) the absolute-index extension the host layer prepared, if it still fits */
-    sh->geo.tw_entries = g->bit_nsamples;
+    sh->geo.tw_entries = sh->mode == 3 ? sh->pfx.fp : g->bit_nsamples;
     sh->slide = 0;
     if (sh->mode == 0 && lc && lc->slide && g->tw_entries > g->bit_nsamples && sh->tw_in_smem) {
 	const size_t extra = (size_t)(g->tw_entries - g->bit_nsamples) * sizeof(float4);
@@ -1586,8 +1756,8 @@ static cudaError_t launch_rx_t(const Shape &sh, const CudaEngine *ce, const fsk_
 	    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh.smem);
     if (e != cudaSuccess)
 	return e;
-    FSK_LAUNCH((k_rx<G, W, L, MODE, FILL, SRC>), sh.blocks, sh.wpb * 32, sh.smem, st, sh.geo, *lc, ce->d_tw,
-	    sh.tw_in_smem, sh.ring, sh.lookahead, a, sh.mplan);
+    FSK_LAUNCH((k_rx<G, W, L, MODE, FILL, SRC>), sh.blocks, sh.wpb * 32, sh.smem, st, sh.geo, *lc,
+	    MODE == 3 ? ce->d_twc : ce->d_tw, sh.tw_in_smem, sh.ring, sh.lookahead, a, sh.mplan, ce->d_tw, sh.pfx);
     g_launches++;
     return cudaGetLastError();
 }
@@ -1621,7 +1791,10 @@ static int rx_batch_any(CudaEngine *ce, const fsk_b200_geom *g, const fsk_b200_l
     if (elem == 2) {
 	if (ce->fill != 0)
 	    return -ENOTSUP;
-	if (sh.mode == 2) {
+	if (sh.mode == 3) {
+	    e = launch_rx_t<32, 1, 1, 3, 0, 1>(sh, ce, lc, a, st);
+	    launched = true;
+	} else if (sh.mode == 2) {
 #define X(GG, WW, LL) if (sh.G == GG && sh.W == WW && sh.L == LL) { e = launch_rx_t<GG, WW, LL, 2, 0, 1>(sh, ce, lc, a, st); launched = true; }
 	    MULTI_COMBOS(X)
 #undef X
@@ -1635,6 +1808,8 @@ static int rx_batch_any(CudaEngine *ce, const fsk_b200_geom *g, const fsk_b200_l
 	}
 	if (!launched)
 	    return -ENOTSUP;
+    } else if (sh.mode == 3) {
+	e = launch_rx_t<32, 1, 1, 3, 0>(sh, ce, lc, a, st);
     } else if (sh.mode == 2) {
 #define X(GG, WW, LL) if (sh.G == GG && sh.W == WW && sh.L == LL) e = launch_rx_t<GG, WW, LL, 2, 0>(sh, ce, lc, a, st);
 	MULTI_COMBOS(X)
@@ -1663,7 +1838,7 @@ static int rx_batch_any(CudaEngine *ce, const fsk_b200_geom *g, const fsk_b200_l
     }
     snprintf(ce->last_kernel, sizeof(ce->last_kernel),
 	    "k_rx<G=%d,W=%d,L=%d,mode=%d(%s),fill=%d,src=%s> threads=%d ring=%u smem=%zu blocks=%d", sh.G, sh.W, sh.L,
-	    sh.mode, sh.mode == 2 ? "shared-segment" : sh.mode == 0 ? "per-candidate" : "generic",
+	    sh.mode, sh.mode == 3 ? "prefix-table" : sh.mode == 2 ? "shared-segment" : sh.mode == 0 ? "per-candidate" : "generic",
 	    sh.mode == 0 ? ce->fill : 0, elem == 2 ? (sh.slide ? "s16,slide" : "s16") : (sh.slide ? "f32,slide" : "f32"),
 	    sh.wpb * 32, sh.ring, sh.smem, sh.blocks);
     if (e != cudaSuccess) {

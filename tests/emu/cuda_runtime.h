@@ -288,6 +288,7 @@ template <class T>
 static inline T __shfl_sync(unsigned mask, T v, int src_lane, int width = 32) { return emu::shfl_idx(mask, v, src_lane, width); }
 static inline int __any_sync(unsigned mask, int pred) { return emu::ballot(mask, pred) != 0u; }
 static inline unsigned __ballot_sync(unsigned mask, int pred) { return emu::ballot(mask, pred); }
+static inline int __ffs(int v) { return __builtin_ffs(v); }
 static inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
 template <class T>
 static inline T __ldg(const T *p) { return *p; }

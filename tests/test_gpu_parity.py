@@ -962,12 +962,27 @@ def test_streams_fed_in_chunks_give_the_records_of_one_pass(mode, kw):
     torch.cuda.synchronize()
     s_end = collect(frames, states)
     assert (s_end["done"] == 1).all()
+    # The per-candidate and shared-segment kernels count the correlation phase from the window (or bit period), so
+    # the arithmetic does not depend on where a stream sits in its row: identical records.  The prefix-table kernel
+    # counts it from the 16-byte chunk that holds the search position, and stream_push moves that: the same sums in
+    # another rounding (a few 1e-7 relative), so bits and positions must still be identical, the statistics close.
+    exact = "prefix-table" not in eng.last_kernel()
     for i in range(nstreams):
         a = np.array(got[i], dtype=mm.FRAME_DTYPE) if got[i] else np.zeros(0, mm.FRAME_DTYPE)
-        assert np.array_equal(a, want[i]), (mode, i, len(a), len(want[i]))
+        if exact:
+            assert np.array_equal(a, want[i]), (mode, i, len(a), len(want[i]))
+            continue
+        assert len(a) == len(want[i]), (mode, i, len(a), len(want[i]))
+        for key in ("bits_lo", "bits_hi", "frame_start"):
+            assert np.array_equal(a[key], want[i][key]), (mode, i, key)
+        for key in ("confidence", "amplitude"):
+            assert np.allclose(a[key], want[i][key], rtol=2e-5, atol=0), (mode, i, key)
     for key in ("carrier", "carrier_nsamples", "nframes_decoded", "confidence_total", "amplitude_total",
                 "noconfidence", "track_amplitude", "peak_confidence"):
-        assert np.array_equal(s_end[key], st_want[key]), key
+        if exact or key in ("carrier", "carrier_nsamples", "nframes_decoded", "noconfidence"):
+            assert np.array_equal(s_end[key], st_want[key]), key
+        else:
+            assert np.allclose(s_end[key], st_want[key], rtol=2e-5, atol=0), key
 
 
 @pytest.mark.parametrize("name", ["small-rtty", "70-callerid-mdmf", "71-callerid-sdmf", "small-same", "small-1200",
@@ -1079,10 +1094,13 @@ def test_per_bit_magnitudes_vs_oracle(mode, kw):
 # (cp.async.bulk + mbarrier, FILL=1) and the warp-synchronous loop (FILL=3), each against the
 # oracle on the same streams
 # --------------------------------------------------------------------------
-@pytest.mark.parametrize("variant", ["multi", "multi-hybrid", "per-candidate", "tma-bulk", "warp-sync"])
+@pytest.mark.parametrize("variant", ["prefix", "multi", "multi-hybrid", "per-candidate", "tma-bulk", "warp-sync"])
 @pytest.mark.parametrize("name", ["01-self-test-1200", "02-self-test-300", "small-rtty"])
 def test_rx_kernel_variants_agree_with_the_oracle(name, variant, monkeypatch):
-    env = {"multi": {"FSK_B200_MULTI": "2"}, "multi-hybrid": {"FSK_B200_MULTI": "1"}, "per-candidate": {"FSK_B200_MULTI": "0"},
+    env = {"prefix": {"FSK_B200_PREFIX": "1"},
+           "multi": {"FSK_B200_MULTI": "2", "FSK_B200_PREFIX": "0"},
+           "multi-hybrid": {"FSK_B200_MULTI": "1", "FSK_B200_PREFIX": "0"},
+           "per-candidate": {"FSK_B200_MULTI": "0", "FSK_B200_PREFIX": "0"},
            "tma-bulk": {"FSK_B200_FILL": "1"}, "warp-sync": {"FSK_B200_FILL": "3"}}[variant]
     import conftest
     if variant == "tma-bulk" and conftest.EMU_DEVICE is not None:
@@ -1099,12 +1117,14 @@ def test_rx_kernel_variants_agree_with_the_oracle(name, variant, monkeypatch):
     streams.append((a + 0.05 * rng.standard_normal(a.size)).astype(np.float32))
     recs, st = rx_on_gpu(eng, streams)
     kern = eng.last_kernel()
-    if variant.startswith("multi"):
+    if variant == "prefix":
+        assert "prefix-table" in kern, kern
+    elif variant.startswith("multi"):
         assert "shared-segment" in kern, kern
     elif variant == "per-candidate":
         assert "per-candidate" in kern, kern
     else:
-        assert "fill=%s" % env["FSK_B200_FILL"] in kern, kern
+        assert "fill=%s" % env["FSK_B200_FILL"] in kern, kern       # (FILL != 0 also keeps the prefix-table search out)
     for s, x in enumerate(streams):
         want = orc.rx_run(rx, x, literal=False)
         compare_frames(as_oracle_frames(recs[s]), want["frames"], "%s %s stream %d" % (name, variant, s))
