@@ -1089,12 +1089,13 @@ __device__ __forceinline__ FoundN find_frame_multi(const Ring rg, unsigned pos_o
 
 /* what a lane needs to know about its place in a candidate slot, computed once per kernel */
 struct PfxLane {
-    unsigned cslot;	/* candidate slot of this lane (>= 32 / bs never: bs divides 32) */
+    unsigned cslot;	/* candidate slot of this lane (== cpr: none, the lane idles) */
     unsigned kk;	/* boundary index inside the slot */
+    unsigned sbase;	/* first lane of the slot */
     unsigned bb;	/* offset of this lane's boundary inside a candidate (0 for an idle lane) */
     unsigned peer;	/* lane that holds the END boundary of this lane's window */
     unsigned exp;	/* expect value (0, 1, 2) of this lane's window: bits 0-1 data string, bits 2-3 sync string */
-    unsigned idx0;	/* rotation-table index of the first chunk of this lane's run (table build) */
+    unsigned idx0;	/* rotation-table index of the first piece of this lane's run (table build) */
     bool win;		/* this lane decides a bit window (kk < n_bits) */
 };
 
@@ -1102,11 +1103,15 @@ __device__ __forceinline__ PfxLane pfx_lane(const fsk_b200_geom &geo, const fsk_
 {
     PfxLane pl;
     const unsigned nb = geo.n_bits, N = geo.bit_nsamples;
-    pl.cslot = lane / pg.bs;
-    pl.kk = lane % pg.bs;
-    pl.win = pl.kk < nb;
+    pl.cslot = min(lane / pg.bs, pg.cpr);
+    pl.kk = lane - pl.cslot * pg.bs;
+    pl.sbase = pl.cslot * pg.bs;
+    const bool in_slot = pl.cslot < pg.cpr;
+    pl.win = in_slot && pl.kk < nb;
     if (pl.win)
 	pl.bb = geo.bit_begin[pl.kk];
+    else if (!in_slot)
+	pl.bb = 0u;
     else if (pg.tiles)
 	pl.bb = pl.kk == nb ? geo.bit_begin[nb - 1u] + N : 0u;
     else
@@ -1114,19 +1119,38 @@ __device__ __forceinline__ PfxLane pfx_lane(const fsk_b200_geom &geo, const fsk_
     pl.peer = (lane + (pg.tiles ? 1u : nb)) & 31u;
     const unsigned e0 = pl.win ? geo.expect[0][pl.kk] : 2u, e1 = pl.win ? geo.expect[1][pl.kk] : 2u;
     pl.exp = e0 | (e1 << 2);
-    pl.idx0 = (pg.s4 * lane * pg.cpl) % pg.fp;
+    pl.idx0 = (pg.s4 * lane * pg.S) % pg.fp;
     return pl;
 }
 
-/* a chunk's four samples against both tones, phase counted from the chunk's first sample:
- * (re, im) mark, (re, im) space.  loc[j-1] = exp(-2 pi i b j / fftsize), j = 1..3 */
-__device__ __forceinline__ float4 pfx_local(float x0, float x1, float x2, float x3, const float (&loc)[3][4])
+/* the chunk-local twiddles exp(-2 pi i b j / fftsize), j = 1..7, held in registers for the table build */
+struct PfxLoc {
+    float v[7][4];
+};
+/* eight samples against both tones, phase counted from the first: (re, im) mark, (re, im) space */
+template <class LOC>
+__device__ __forceinline__ float4 pfx_local(const float4 a, const float4 b, const LOC &loc)
 {
     float4 s;
-    s.x = fmaf(x3, loc[2][0], fmaf(x2, loc[1][0], fmaf(x1, loc[0][0], x0)));
-    s.y = fmaf(x3, loc[2][1], fmaf(x2, loc[1][1], x1 * loc[0][1]));
-    s.z = fmaf(x3, loc[2][2], fmaf(x2, loc[1][2], fmaf(x1, loc[0][2], x0)));
-    s.w = fmaf(x3, loc[2][3], fmaf(x2, loc[1][3], x1 * loc[0][3]));
+    s.x = fmaf(b.w, loc[6][0], fmaf(b.z, loc[5][0], fmaf(b.y, loc[4][0], fmaf(b.x, loc[3][0],
+	    fmaf(a.w, loc[2][0], fmaf(a.z, loc[1][0], fmaf(a.y, loc[0][0], a.x)))))));
+    s.y = fmaf(b.w, loc[6][1], fmaf(b.z, loc[5][1], fmaf(b.y, loc[4][1], fmaf(b.x, loc[3][1],
+	    fmaf(a.w, loc[2][1], fmaf(a.z, loc[1][1], a.y * loc[0][1]))))));
+    s.z = fmaf(b.w, loc[6][2], fmaf(b.z, loc[5][2], fmaf(b.y, loc[4][2], fmaf(b.x, loc[3][2],
+	    fmaf(a.w, loc[2][2], fmaf(a.z, loc[1][2], fmaf(a.y, loc[0][2], a.x)))))));
+    s.w = fmaf(b.w, loc[6][3], fmaf(b.z, loc[5][3], fmaf(b.y, loc[4][3], fmaf(b.x, loc[3][3],
+	    fmaf(a.w, loc[2][3], fmaf(a.z, loc[1][3], a.y * loc[0][3]))))));
+    return s;
+}
+/* the same for a single piece (the last chunk of a run) */
+template <class LOC>
+__device__ __forceinline__ float4 pfx_local4(const float4 a, const LOC &loc)
+{
+    float4 s;
+    s.x = fmaf(a.w, loc[2][0], fmaf(a.z, loc[1][0], fmaf(a.y, loc[0][0], a.x)));
+    s.y = fmaf(a.w, loc[2][1], fmaf(a.z, loc[1][1], a.y * loc[0][1]));
+    s.z = fmaf(a.w, loc[2][2], fmaf(a.z, loc[1][2], fmaf(a.y, loc[0][2], a.x)));
+    s.w = fmaf(a.w, loc[2][3], fmaf(a.z, loc[1][3], a.y * loc[0][3]));
     return s;
 }
 /* acc += rot * s, tone by tone (complex) */
@@ -1138,60 +1162,131 @@ __device__ __forceinline__ void pfx_rot_acc(float4 &acc, const float4 rt, const 
     acc.w = fmaf(rt.w, s.z, fmaf(rt.z, s.w, acc.w));
 }
 
-/* The table of one search span: chunk m = ring floats [base + 4m, base + 4m + 4) (base = ring offset of the
- * 16-byte chunk that holds the search position).  Lane g walks the chunks [g * cpl, (g + 1) * cpl) in
- * order, stores the sum of its EARLIER chunks in pre[m] and its total in tot[g]. */
-__device__ __forceinline__ void pfx_build(const float *ring, unsigned R, unsigned base, unsigned nchunks,
+/* The table of one search span.  Piece q = ring floats [base + 4q, base + 4q + 4) (base = ring offset of the
+ * 16-byte piece that holds the search position), npieces of them are needed.  Lane g walks the pieces
+ * [g * S, (g + 1) * S) two at a time (the last chunk of a run is a single piece: S is odd), stores the sum
+ * of the run's EARLIER chunks in pre[g * tstride + c] and the run's total in tot[g].  The head of the ring
+ * is mirrored behind its end for the length of a run and the rotation table is staged a run longer than
+ * its period, so a run is three linear walks: no wrap tests. */
+__device__ __forceinline__ void pfx_build(const float *ring, unsigned R, unsigned base, unsigned npieces,
 	float4 *pre, float4 *tot, const float4 *twc, const fsk_b200_pfx &pg, const PfxLane &pl, unsigned lane)
 {
-    const unsigned m0 = lane * pg.cpl;
-    const unsigned m1 = min(m0 + pg.cpl, nchunks);
-    unsigned off = base + 4u * m0;
+    const unsigned S = pg.S, q0 = lane * S;
+    const unsigned avail = q0 < npieces ? min(S, npieces - q0) : 0u;	/* pieces of this run that are needed */
+    const unsigned nfull = min((avail + 1u) >> 1, (S - 1u) >> 1);	/* (a trailing piece nobody needs rides along) */
+    unsigned off = base + 4u * q0;
     if (off >= R)
 	off -= R;
-    unsigned idx = pl.idx0;
+    const float4 *xp = reinterpret_cast<const float4 *>(ring + off);
+    const float4 *tp = twc + pl.idx0;
+    const unsigned step2 = 2u * pg.s4;
+    float4 *row = pre + lane * pg.tstride;
+    PfxLoc lc;
+#pragma unroll
+    for (int j = 0; j < 7; j++)
+#pragma unroll
+	for (int k = 0; k < 4; k++)
+	    lc.v[j][k] = pg.loc[j][k];
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 2
-    for (unsigned m = m0; m < m1; m++) {
-	const float4 x = *reinterpret_cast<const float4 *>(ring + off);
-	const float4 rt = twc[idx];
-	pre[m] = acc;
-	pfx_rot_acc(acc, rt, pfx_local(x.x, x.y, x.z, x.w, pg.loc));
-	off += 4u;
-	if (off == R)
-	    off = 0u;
-	idx += pg.s4;
-	if (idx >= pg.fp)
-	    idx -= pg.fp;
+#pragma unroll 4
+    for (unsigned c = 0; c < nfull; c++) {
+	const float4 xa = xp[0], xb = xp[1];
+	const float4 rt = *tp;
+	row[c] = acc;
+	pfx_rot_acc(acc, rt, pfx_local(xa, xb, lc.v));
+	xp += 2;
+	tp += step2;
+    }
+    if (avail == S) {				/* the run's last chunk is a single piece */
+	const float4 xa = xp[0];
+	const float4 rt = *tp;
+	row[nfull] = acc;
+	pfx_rot_acc(acc, rt, pfx_local4(xa, lc.v));
     }
     tot[lane] = acc;
 }
 
-/* One round: the candidates `t` of the 32 / bs slots (valid or not, per slot), every window of every one
+/* Sums over the lanes of a candidate slot; every lane of the slot ends with the total.  LB > 0: the slot is
+ * 1 << LB lanes, aligned (butterfly); LB == 0: any slot size (pg.bs), packed back to back. */
+template <int LB>
+__device__ __forceinline__ void pfx_slot_sum4(float &a, float &b, float &c, unsigned &d, const fsk_b200_pfx &pg,
+	const PfxLane &pl, unsigned lane)
+{
+    const unsigned FULL = 0xffffffffu;
+    if (LB > 0) {
+#pragma unroll
+	for (int o = (1 << LB) >> 1; o; o >>= 1) {
+	    a += __shfl_xor_sync(FULL, a, o);
+	    b += __shfl_xor_sync(FULL, b, o);
+	    c += __shfl_xor_sync(FULL, c, o);
+	    d += __shfl_xor_sync(FULL, d, o);
+	}
+    } else {
+	for (unsigned o = 1; o < pg.bs; o <<= 1) {
+	    const unsigned src = min(lane + o, 31u);
+	    const bool ok = pl.kk + o < pg.bs;
+	    const float a2 = __shfl_sync(FULL, a, src), b2 = __shfl_sync(FULL, b, src), c2 = __shfl_sync(FULL, c, src);
+	    const unsigned d2 = __shfl_sync(FULL, d, src);
+	    a += ok ? a2 : 0.f;
+	    b += ok ? b2 : 0.f;
+	    c += ok ? c2 : 0.f;
+	    d += ok ? d2 : 0u;
+	}
+	a = __shfl_sync(FULL, a, pl.sbase);
+	b = __shfl_sync(FULL, b, pl.sbase);
+	c = __shfl_sync(FULL, c, pl.sbase);
+	d = __shfl_sync(FULL, d, pl.sbase);
+    }
+}
+template <int LB>
+__device__ __forceinline__ float pfx_slot_sum1(float a, const fsk_b200_pfx &pg, const PfxLane &pl, unsigned lane)
+{
+    const unsigned FULL = 0xffffffffu;
+    if (LB > 0) {
+#pragma unroll
+	for (int o = (1 << LB) >> 1; o; o >>= 1)
+	    a += __shfl_xor_sync(FULL, a, o);
+	return a;
+    }
+    for (unsigned o = 1; o < pg.bs; o <<= 1) {
+	const float a2 = __shfl_sync(FULL, a, min(lane + o, 31u));
+	a += pl.kk + o < pg.bs ? a2 : 0.f;
+    }
+    return __shfl_sync(FULL, a, pl.sbase);
+}
+
+/* One round: the candidates `t` of the cpr slots (valid or not, per slot), every window of every one
  * of them from the table.  All 32 lanes take part (full-mask shuffles).  Returns this slot's
  * confidence (0 for an invalid slot or a rejected candidate); all lanes of a slot hold the same values. */
+template <int LB>
 __device__ __forceinline__ float pfx_round(const float *ring, unsigned R, unsigned base, unsigned r0, unsigned t,
 	bool valid, const float4 *pre, const float4 *tot, const float4 *twc, const float4 *__restrict__ tw_sample,
-	const fsk_b200_pfx &pg, const fsk_b200_geom &geo, const PfxLane &pl, int sel,
+	const fsk_b200_pfx &pg, const fsk_b200_geom &geo, const PfxLane &pl, int sel, unsigned lane,
 	unsigned &bits_lo_out, unsigned &bits_hi_out, float &ampl_out, float2 *bit_mags = nullptr)
 {
     const unsigned FULL = 0xffffffffu;
     const unsigned N = geo.bit_nsamples, nb = geo.n_bits;
-    /* this lane's boundary: sample i of the span, r samples into chunk m */
+    /* this lane's boundary: sample i of the span, in piece q = run l_b, piece o4 of the run; r samples of
+     * the boundary's chunk (pieces qa, qa + 1) precede it */
     const unsigned i = r0 + (valid ? t : 0u) + pl.bb;
-    const unsigned m = i >> 2, r = i & 3u;
-    unsigned off = base + (i & ~3u);
-    if (off >= R)
-	off -= R;
-    const float4 x = *reinterpret_cast<const float4 *>(ring + off);
-    const unsigned sm = pg.s4 * m;
+    const unsigned q = i >> 2;
+    const unsigned l_b = (unsigned)(((float)q + 0.5f) * pg.inv_S);
+    const unsigned o4 = q - l_b * pg.S;
+    const unsigned r = ((o4 & 1u) << 2) | (i & 3u);
+    const unsigned qa = q - (o4 & 1u);
+    unsigned offa = base + 4u * qa;
+    if (offa >= R)
+	offa -= R;
+    const float4 xa = *reinterpret_cast<const float4 *>(ring + offa);
+    const float4 xb = *reinterpret_cast<const float4 *>(ring + offa + 4u);	/* (the mirror covers a read across the end) */
+    const unsigned sm = pg.s4 * qa;
     const unsigned idx = sm - (unsigned)(((float)sm + 0.5f) * pg.inv_fp) * pg.fp;
     const float4 rt = twc[idx];
-    float4 P = pre[m];
-    const unsigned l_b = (unsigned)(((float)m + 0.5f) * pg.inv_cpl);
-    /* the r samples of the boundary's own chunk that precede it (a chunk past the requested samples is
-     * only ever met with r == 0: nothing of it is used) */
-    pfx_rot_acc(P, rt, pfx_local(r > 0u ? x.x : 0.f, r > 1u ? x.y : 0.f, r > 2u ? x.z : 0.f, 0.f, pg.loc));
+    float4 P = pre[l_b * pg.tstride + (o4 >> 1)];
+    /* (pieces past the requested samples, or of the next run, are only ever met with r too small to use them) */
+    pfx_rot_acc(P, rt, pfx_local(
+	    make_float4(r > 0u ? xa.x : 0.f, r > 1u ? xa.y : 0.f, r > 2u ? xa.z : 0.f, r > 3u ? xa.w : 0.f),
+	    make_float4(r > 4u ? xb.x : 0.f, r > 5u ? xb.y : 0.f, r > 6u ? xb.z : 0.f, 0.f), pg.loc));
     /* the end of this lane's window is another lane's boundary */
     float4 S;
     S.x = __shfl_sync(FULL, P.x, pl.peer) - P.x;
@@ -1209,63 +1304,58 @@ __device__ __forceinline__ float pfx_round(const float *ring, unsigned R, unsign
     /* per-window decision (src/fsk.c:158-169) and this lane's share of the sums (:271-289); magnitudes stay
      * unscaled as in frame_finish */
     const float eps_u = geo.eps_unscaled;
-    float tn = 0.f, am = 0.f, as = 0.f, sig = 0.f;
-    unsigned nm = 0, blo = 0, bhi = 0;
-    bool one = false;
-    if (own) {
-	float mag_mark = fast_sqrt(S.x * S.x + S.y * S.y);
-	float mag_space = fast_sqrt(S.z * S.z + S.w * S.w);
-	const float mag_hi = fmaxf(mag_mark, mag_space);
-	if (mag_hi != 0.f && fminf(mag_mark, mag_space) < eps_u + 2e-6f * mag_hi) {
-	    /* too close to the :279 threshold for fp32 sums (see needs_resum): the window again, in fp64, phase
-	     * counted from its first sample (the per-sample table, from global memory: rare) */
-	    double drm = 0., dim = 0., drs = 0., dis = 0.;
-	    unsigned q = base + i;
-	    if (q >= R)
-		q -= R;
+    float mag_mark = fast_sqrt(S.x * S.x + S.y * S.y);
+    float mag_space = fast_sqrt(S.z * S.z + S.w * S.w);
+    const float mag_hi = fmaxf(mag_mark, mag_space);
+    if (own && mag_hi != 0.f && fminf(mag_mark, mag_space) < eps_u + 2e-6f * mag_hi) {
+	/* too close to the :279 threshold for fp32 sums (see needs_resum): the window again, in fp64, phase
+	 * counted from its first sample (the per-sample table, from global memory: rare) */
+	double drm = 0., dim = 0., drs = 0., dis = 0.;
+	unsigned qq = base + i;
+	if (qq >= R)
+	    qq -= R;
 #pragma unroll 1
-	    for (unsigned n = 0; n < N; n++) {
-		const double xs = (double)ring[q];
-		const float4 c = __ldg(tw_sample + n);
-		drm = fma(xs, (double)c.x, drm);
-		dim = fma(xs, (double)c.y, dim);
-		drs = fma(xs, (double)c.z, drs);
-		dis = fma(xs, (double)c.w, dis);
-		if (++q == R)
-		    q = 0u;
-	    }
-	    const float frm = (float)drm, fim = (float)dim, frs = (float)drs, fis = (float)dis;
-	    mag_mark = sqrtf(frm * frm + fim * fim);
-	    mag_space = sqrtf(frs * frs + fis * fis);
+	for (unsigned n = 0; n < N; n++) {
+	    const double xs = (double)ring[qq];
+	    const float4 c = __ldg(tw_sample + n);
+	    drm = fma(xs, (double)c.x, drm);
+	    dim = fma(xs, (double)c.y, dim);
+	    drs = fma(xs, (double)c.z, drs);
+	    dis = fma(xs, (double)c.w, dis);
+	    if (++qq == R)
+		qq = 0u;
 	}
-	one = mag_mark > mag_space;				/* strict: tie -> space */
-	sig = one ? mag_mark : mag_space;
-	const float noise = one ? mag_space : mag_mark;
-	const unsigned e = (pl.exp >> (sel ? 2 : 0)) & 3u;
-	if (bit_mags)
-	    bit_mags[pl.kk] = make_float2(sig * geo.mag_scalar, noise * geo.mag_scalar);
-	if (noise > eps_u)					/* :279 */
-	    tn = noise;
-	if (e != 2u && e != (one ? 1u : 0u))			/* pass 1, :211: poisons the noise sum */
-	    tn = INFINITY;
-	if (one) {
-	    am = sig;
-	    nm = 1u;
-	    if (pl.kk < 32u) blo = 1u << pl.kk; else bhi = 1u << (pl.kk - 32u);
-	} else
-	    as = sig;
+	const float frm = (float)drm, fim = (float)dim, frs = (float)drs, fis = (float)dis;
+	mag_mark = sqrtf(frm * frm + fim * fim);
+	mag_space = sqrtf(frs * frs + fis * fis);
     }
-    /* the frame sums over the lanes of the slot (src/fsk.c:271-289) */
-    for (unsigned o = pg.bs >> 1; o; o >>= 1) {
-	tn += __shfl_xor_sync(FULL, tn, o);
-	am += __shfl_xor_sync(FULL, am, o);
-	as += __shfl_xor_sync(FULL, as, o);
-	nm += __shfl_xor_sync(FULL, nm, o);
-	blo |= __shfl_xor_sync(FULL, blo, o);
+    const bool one = mag_mark > mag_space;			/* strict: tie -> space */
+    const float sig = own ? (one ? mag_mark : mag_space) : 0.f;
+    const float noise = one ? mag_space : mag_mark;
+    const unsigned e = (pl.exp >> (sel ? 2 : 0)) & 3u;		/* (2 for a lane without a window) */
+    if (bit_mags && own)
+	bit_mags[pl.kk] = make_float2(sig * geo.mag_scalar, noise * geo.mag_scalar);
+    float tn = (own && noise > eps_u) ? noise : 0.f;		/* :279 */
+    if (own && e != 2u && e != (one ? 1u : 0u))			/* pass 1, :211: poisons the noise sum */
+	tn = INFINITY;
+    const bool mark = own && one;
+    float am = mark ? sig : 0.f, as = mark ? 0.f : sig;
+    unsigned nm, blo = mark && pl.kk < 32u ? 1u << (pl.kk & 31u) : 0u, bhi = mark && pl.kk >= 32u ? 1u << (pl.kk & 31u) : 0u;
+    /* the frame sums over the lanes of the slot (src/fsk.c:271-289); the mark count rides above the bits
+     * (disjoint bit positions: OR == ADD) when the frame is short enough */
+    if (nb <= 24u) {
+	unsigned packed = blo | (mark ? 1u << 24 : 0u);
+	pfx_slot_sum4<LB>(tn, am, as, packed, pg, pl, lane);
+	blo = packed & 0xffffffu;
+	nm = packed >> 24;
+    } else {
+	float z0 = 0.f, z1 = 0.f, z2 = 0.f;
+	nm = mark ? 1u : 0u;
+	pfx_slot_sum4<LB>(tn, am, as, nm, pg, pl, lane);
+	/* bit positions are disjoint, so the words add like they OR */
+	pfx_slot_sum4<LB>(z0, z1, z2, blo, pg, pl, lane);
+	pfx_slot_sum4<LB>(z0, z1, z2, bhi, pg, pl, lane);
     }
-    if (nb > 32u)
-	for (unsigned o = pg.bs >> 1; o; o >>= 1)
-	    bhi |= __shfl_xor_sync(FULL, bhi, o);
     const float ts = am + as;
     const unsigned n_space = nb - nm;
     const float snr = fast_div(ts, tn);					/* :292, may be +inf */
@@ -1274,13 +1364,9 @@ __device__ __forceinline__ float pfx_round(const float *ring, unsigned R, unsign
 	am = fast_div(am, (float)nm);					/* :298-301 */
     if (n_space)
 	as = fast_div(as, (float)n_space);
-    float dv = 0.f;							/* :305-311 */
-    if (own) {
-	const float other = one ? am : as;
-	dv = fast_div(fabsf(sig - other), other);
-    }
-    for (unsigned o = pg.bs >> 1; o; o >>= 1)
-	dv += __shfl_xor_sync(FULL, dv, o);
+    const float other = one ? am : as;					/* :305-311 */
+    float dv = own ? fast_div(fabsf(sig - other), other) : 0.f;
+    dv = pfx_slot_sum1<LB>(dv, pg, pl, lane);
     const float divergence = dv * 2.f * geo.inv_n_bits;		/* :312-313 */
     if (!valid || tn == INFINITY) {					/* pass 1 reject, :211-212 */
 	bits_lo_out = bits_hi_out = 0u;
@@ -1295,24 +1381,23 @@ __device__ __forceinline__ float pfx_round(const float *ring, unsigned R, unsign
 
 /* fsk_find_frame (src/fsk.c:449-538) over the table: the candidates in the reference's visiting order
  * (first, +1, -1, +2, -2, ... steps; the scan ends at the first upward step that reaches try_max, and
- * downward steps below 0 are skipped), 32 / bs of them per round.  The reference returns the first
- * candidate in that order whose confidence reaches `limit` (everything before it was below the limit, so
- * it is also the best so far), else the largest confidence, the earliest among equals (:492 is strict). */
+ * downward steps below 0 are skipped: fsk_b200_pfx_kind), cpr of them per round.  The reference returns
+ * the first candidate in that order whose confidence reaches `limit` (everything before it was below the
+ * limit, so it is also the best so far), else the largest confidence, the earliest among equals (:492 is
+ * strict). */
+template <int LB>
 __device__ __forceinline__ Found pfx_search(const float *ring, unsigned R, unsigned base, unsigned r0,
 	const float4 *pre, const float4 *tot, const float4 *twc, const float4 *__restrict__ tw_sample,
 	const fsk_b200_pfx &pg, const fsk_b200_geom &geo, const PfxLane &pl, int sel, unsigned try_first,
-	unsigned try_max, unsigned step, float limit, unsigned lane, unsigned &ncand)
+	const fsk_b200_pfx_kind &kd, float limit, unsigned lane, unsigned &ncand)
 {
     const unsigned FULL = 0xffffffffu;
-    const unsigned cpr = 32u / pg.bs;
-    const unsigned k_up = (try_max - 1u - try_first) / step;
-    const unsigned k_dn = min(try_first / step, k_up);
-    const unsigned ncands = 1u + k_up + k_dn;
+    const unsigned cpr = pg.cpr, k_dn = kd.k_dn, ncands = kd.ncands, step = kd.step;
     Found best = { 0.f, 0.f, 0u, 0u, 0u };
 #pragma unroll 1
     for (unsigned o0 = 0; o0 < ncands; o0 += cpr) {
 	const unsigned o = o0 + pl.cslot;
-	const bool valid = o < ncands;
+	const bool valid = pl.cslot < cpr && o < ncands;
 	/* the o-th candidate of the visiting order */
 	unsigned t = try_first;
 	if (o > 2u * k_dn)
@@ -1323,7 +1408,7 @@ __device__ __forceinline__ Found pfx_search(const float *ring, unsigned R, unsig
 	    t = try_first - (o >> 1) * step;
 	unsigned lo, hi;
 	float a;
-	float c = pfx_round(ring, R, base, r0, t, valid, pre, tot, twc, tw_sample, pg, geo, pl, sel, lo, hi, a);
+	float c = pfx_round<LB>(ring, R, base, r0, t, valid, pre, tot, twc, tw_sample, pg, geo, pl, sel, lane, lo, hi, a);
 	if (!(c > 0.f))
 	    c = 0.f;					/* NaN and negatives never win (:492) */
 	ncand += min(cpr, ncands - o0);
@@ -1335,22 +1420,22 @@ __device__ __forceinline__ Found pfx_search(const float *ring, unsigned R, unsig
 	    src = (unsigned)__ffs((int)reach) - 1u;
 	else {
 	    float cm = c;
-	    for (unsigned d = pg.bs; d < 32u; d <<= 1)
+#pragma unroll
+	    for (unsigned d = 16u; d; d >>= 1)
 		cm = fmaxf(cm, __shfl_xor_sync(FULL, cm, d));
 	    src = (unsigned)__ffs((int)__ballot_sync(FULL, c == cm)) - 1u;
 	}
 	const float cw = __shfl_sync(FULL, c, src);
-	const float aw = __shfl_sync(FULL, a, src);
-	const unsigned tw_ = __shfl_sync(FULL, t, src);
-	const unsigned low = __shfl_sync(FULL, lo, src);
-	const unsigned hiw = __shfl_sync(FULL, hi, src);
 	if (best.confidence < cw) {
-	    best = Found{ cw, aw, tw_, low, hiw };
+	    best.confidence = cw;
+	    best.amplitude = __shfl_sync(FULL, a, src);
+	    best.start = __shfl_sync(FULL, t, src);
+	    best.bits_lo = __shfl_sync(FULL, lo, src);
+	    best.bits_hi = __shfl_sync(FULL, hi, src);
 	    if (cw >= limit)
 		break;					/* :499 */
 	}
     }
-    (void)lane;
     return best;
 }
 

@@ -78,23 +78,33 @@ int fsk_b200_mplan_build(const fsk_b200_geom *g, const struct fsk_b200_loopc *lc
 
 /* ---- chunk-prefix table search (the "prefix" rx kernel, k_rx MODE 3) ------------------------------
  * Once per rx-loop iteration the 32 lanes of a stream's warp demodulate the whole search span
- * (try_max - 1 + span samples) against both tones in 4-sample chunks -- every sample is multiplied once,
- * whatever the number of candidates the coarse and the fine search then visit -- and leave, per chunk,
- * the running sums of the lane's run of chunks (exclusive prefix) plus one total per lane-run.  A bit
- * window of ANY candidate is then the difference of two boundary values (prefix + at most three samples
- * of the boundary's own chunk) plus the totals of the runs in between: a handful of loads instead of
- * bit_nsamples multiply-adds.  The phase is absolute (counted from the chunk that holds the search
- * position), which changes a window's sums by a unit factor only (src/fsk.c:107-114 takes the magnitude). */
+ * (try_max - 1 + span samples) against both tones -- every sample is multiplied once, whatever the number
+ * of candidates the coarse and the fine search then visit.  Lane g walks its RUN of S consecutive 16-byte
+ * pieces of the ring (S odd: the lanes' accesses then spread over all shared-memory banks) in chunks of 8
+ * samples (the last chunk of a run holds 4) and leaves, per chunk, the sum of the run's earlier chunks,
+ * plus one total per run.  A bit window of ANY candidate is then the difference of two boundary values
+ * (the chunk's prefix + the at most seven samples of the boundary's own chunk) plus the totals of the runs
+ * in between: a handful of loads instead of bit_nsamples multiply-adds.  The phase is absolute (counted
+ * from the 16-byte piece that holds the search position), which changes a window's sums by a unit factor
+ * only (src/fsk.c:107-114 takes the magnitude). */
+typedef struct fsk_b200_pfx_kind {	/* one search of the rx loop: the candidate set of src/fsk.c:477-484 */
+    uint32_t	k_up, k_dn;		/* try_first + k * step for -k_dn <= k <= k_up */
+    uint32_t	ncands;			/* 1 + k_up + k_dn */
+    uint32_t	step;
+} fsk_b200_pfx_kind;
 typedef struct fsk_b200_pfx {
     uint32_t	nbnd;		/* boundaries per candidate: n_bits + 1 when the windows tile, else 2 * n_bits (begin, end) */
-    uint32_t	bs;		/* lanes per candidate slot: the power of two >= nbnd; 32 / bs candidates are analysed side by side */
+    uint32_t	bs;		/* lanes per candidate slot (= nbnd); cpr = 32 / bs candidates are analysed side by side */
+    uint32_t	cpr;
+    uint32_t	pow2;		/* bs is a power of two: butterfly reductions */
     uint32_t	tiles;		/* 1: window w ends where window w + 1 begins */
-    uint32_t	cpl;		/* chunks per lane-run of the table build: ceil(nchunks / 32) */
-    float	inv_cpl;
-    uint32_t	fp, s4;		/* chunk m is rotated by table entry (s4 * m) mod fp: fp = fftsize / gcd(4, fftsize), s4 = 4 / gcd */
+    uint32_t	S;		/* 16-byte pieces per lane-run (odd) */
+    float	inv_S;
+    uint32_t	tstride;	/* table entries per lane-run: (S + 1) / 2 chunks, made odd */
+    uint32_t	fp, s4;		/* the piece at index q is rotated by table entry (s4 * q) mod fp: fp = fftsize / gcd(4, fftsize), s4 = 4 / gcd */
     float	inv_fp;
-    uint32_t	nchunks;	/* table capacity per stream: (3 + try_max - 1 + span) / 4 + 1 for the widest search */
-    float	loc[3][4];	/* exp(-2 pi i b j / fftsize), j = 1..3, as (re, im) for b_mark, b_space: the samples of a chunk */
+    float	loc[7][4];	/* exp(-2 pi i b j / fftsize), j = 1..7, as (re, im) for b_mark, b_space: the samples of a chunk */
+    fsk_b200_pfx_kind kind[4];	/* [carrier + 2 * fine], as fsk_b200_mplan.kind */
 } fsk_b200_pfx;
 
 void fsk_b200_set_error(const char *fmt, ...);

@@ -246,10 +246,12 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
 	const float4 *__restrict__ tw_sample, const __grid_constant__ fsk_b200_pfx pg)
 {
     FSK_DYN_SMEM(smem4);
-    /* MODE 3 (chunk-prefix table): no window is ever walked linearly, so the ring has no mirror; the staged
-     * table (tw_global) is the chunk-rotation table, the per-sample one stays in global memory (tw_sample) */
-    const unsigned ring_pad = MODE == 3 ? 0u : (geo.bit_nsamples + 3u) & ~3u;
-    const Smem sm = carve<G>(smem4, geo, tw_global, tw_in_smem, ring_floats, ring_pad, MODE == 3 ? pg.nchunks : 0u);
+    /* MODE 3 (chunk-prefix table): the ring's mirror covers one lane-run of the table build (not a bit window);
+     * the staged table (tw_global) is the chunk-rotation table, the per-sample one stays in global memory
+     * (tw_sample) */
+    const unsigned ring_pad = MODE == 3 ? 4u * pg.S + 8u : (geo.bit_nsamples + 3u) & ~3u;
+    constexpr int LB = W == 1 ? 0 : W;		/* MODE 3: log2 of the candidate slot (0: packed slots of any size) */
+    const Smem sm = carve<G>(smem4, geo, tw_global, tw_in_smem, ring_floats, ring_pad, MODE == 3 ? 32u * pg.tstride : 0u);
     GROUP_VARS;
     const Ring rg = { smem_u32(sm.ring), ring_floats, ring_pad };
     const unsigned tw_s = tw_in_smem ? smem_u32(sm.tw) : 0u;	/* the fast path requires the table in shared memory */
@@ -488,8 +490,8 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
 				    twc, pg, pfl, lane);
 			    __syncwarp(gmask);
 			}
-			f = pfx_search(ringp, R, base, pos_off & 3u, pre, tot, twc, tw_sample, pg, geo, pfl, which,
-				try_first, try_max, step, limit, lane, ncand);
+			f = pfx_search<LB>(ringp, R, base, pos_off & 3u, pre, tot, twc, tw_sample, pg, geo, pfl, which,
+				try_first, pg.kind[(carrier ? 1 : 0) + (pass ? 2 : 0)], limit, lane, ncand);
 		    } else if (MODE == 2) {
 			/* :1265, :1378 from shared segment sums.  Which plan: the window is the one chosen at the
 			 * top of the iteration (carrier then), coarse or fine.  A coarse search in the steady
@@ -1175,6 +1177,7 @@ struct CudaEngine {
     int lanes, wpb, ring, split, fill;
     char last_kernel[160];	/* what the latest rx / find_frame launch ran (diagnostics) */
     int multi;			/* 1 (default): shared-segment search where the mode allows it; 0: always per candidate */
+    int pfx_fill;		/* mode 3, float rows: 1 (default) TMA bulk fill, 0 cp.async fill */
     int prefix;			/* chunk-prefix table search (mode 3): -1 (default) where it pays, 0 never, 1 wherever it fits */
     float4 *d_twc;		/* mode 3: chunk-rotation table, twc_n = fftsize / gcd(4, fftsize) entries (0: not built) */
     unsigned twc_n, twc_cap;
@@ -1237,6 +1240,11 @@ extern "C" void *fsk_b200_cuda_engine_new(void)
      * 1 wherever the mode fits it */
     ce->prefix = -1;
     if ((e = getenv("FSK_B200_PREFIX"))) ce->prefix = atoi(e);
+    ce->pfx_fill = 1;
+    if ((e = getenv("FSK_B200_PFX_FILL"))) ce->pfx_fill = atoi(e) ? 1 : 0;
+#ifdef FSK_EMU
+    ce->pfx_fill = 0;		/* the host emulation of the test harness does not model cp.async.bulk / mbarrier */
+#endif
     /* 256 MiB of samples ON THE WIRE per slab, two slabs in flight: the float path runs at the PCIe
      * rate with that (54 GB/s).  The int16 path, measured with slabs of the same stream count (128 MiB
      * on the wire), reached 78 % of it -- about 0.7 ms per slab stayed exposed (one conversion plus
@@ -1306,6 +1314,7 @@ extern "C" int fsk_b200_cuda_tune(void *p, int lanes, int wpb, int ring)
 }
 
 #define FSK_PFX_MAX_TABLE_BYTES (16u * 1024u)
+#define FSK_PFX_TABLE_EXTRA 2056u	/* rotation-table entries past one period (a lane-run of up to 512 pieces, s4 <= 4) */
 #ifndef FSK_PREFIX_MIN_N
 #define FSK_PREFIX_MIN_N 170u	/* shortest bit period (samples) for which mode 3 is the default (measured: RTTY @8 kHz, 176) */
 #endif
@@ -1368,11 +1377,14 @@ extern "C" int fsk_b200_cuda_set_table(void *p, int fftsize, unsigned b_mark, un
 	const unsigned g4 = (fftsize % 4 == 0) ? 4u : (fftsize % 2 == 0) ? 2u : 1u;
 	const unsigned fp = (unsigned)fftsize / g4;
 	if ((size_t)fp * sizeof(float4) <= FSK_PFX_MAX_TABLE_BYTES) {
-	    float4 *hc = (float4 *)malloc(sizeof(float4) * fp);
+	    /* (FSK_PFX_TABLE_EXTRA entries more than one period: a lane-run of the table build walks it
+	     * linearly from anywhere inside the period) */
+	    const unsigned fp1 = fp, fpx = fp + FSK_PFX_TABLE_EXTRA;
+	    float4 *hc = (float4 *)malloc(sizeof(float4) * fpx);
 	    if (!hc)
 		return -ENOMEM;
-	    for (unsigned i = 0; i < fp; i++) {
-		const unsigned long long n = (unsigned long long)i * g4;
+	    for (unsigned i = 0; i < fpx; i++) {
+		const unsigned long long n = (unsigned long long)(i % fp1) * g4;
 		const double am = 2.0 * M_PI * (double)(((unsigned long long)b_mark * n) % F) / (double)F;
 		const double as = 2.0 * M_PI * (double)(((unsigned long long)b_space * n) % F) / (double)F;
 		hc[i].x = (float)cos(am);
@@ -1380,18 +1392,18 @@ extern "C" int fsk_b200_cuda_set_table(void *p, int fftsize, unsigned b_mark, un
 		hc[i].z = (float)cos(as);
 		hc[i].w = (float)-sin(as);
 	    }
-	    if (ce->twc_cap < fp) {
+	    if (ce->twc_cap < fpx) {
 		cudaFree(ce->d_twc);
 		ce->d_twc = NULL;
 		ce->twc_cap = 0;
-		if (cudaMalloc(&ce->d_twc, sizeof(float4) * fp) != cudaSuccess) {
+		if (cudaMalloc(&ce->d_twc, sizeof(float4) * fpx) != cudaSuccess) {
 		    (void)cudaGetLastError();
 		    free(hc);
 		    return 0;			/* mode 3 is simply not offered */
 		}
-		ce->twc_cap = fp;
+		ce->twc_cap = fpx;
 	    }
-	    cudaError_t err2 = cudaMemcpy(ce->d_twc, hc, sizeof(float4) * fp, cudaMemcpyHostToDevice);
+	    cudaError_t err2 = cudaMemcpy(ce->d_twc, hc, sizeof(float4) * fpx, cudaMemcpyHostToDevice);
 	    if (err2 == cudaSuccess)
 		err2 = cudaDeviceSynchronize();
 	    free(hc);
@@ -1413,6 +1425,7 @@ struct Shape {
     fsk_b200_geom geo;
     fsk_b200_mplan mplan;	/* mode 2 */
     fsk_b200_pfx pfx;		/* mode 3 */
+    unsigned pfx_tw_stage;	/* mode 3: rotation-table entries staged per block */
     unsigned slide;		/* mode 0: fine searches by sliding (extended twiddle table staged) */
 };
 
@@ -1436,6 +1449,10 @@ struct Shape {
 #define MULTI_COMBOS(X) \
     X(8, 2, 2) X(8, 3, 2) X(8, 4, 2) X(16, 2, 2) X(16, 3, 2) X(16, 4, 2) X(16, 2, 4) X(16, 3, 4) X(16, 4, 4) \
     X(32, 2, 4) X(32, 3, 4) X(32, 4, 4)
+
+/* mode 3: the W of k_rx<32, W, 1, 3> codes the candidate slot: 1 = packed slots of nbnd lanes, 3 / 4 / 5 = aligned
+ * slots of 8 / 16 / 32 lanes */
+#define PFX_SLOTS(X) X(1) X(3) X(4) X(5)
 
 /* per-candidate shapes that are also built for int16 rows (SRC 1); every MULTI_COMBOS shape is */
 #define S16_FAST_COMBOS(X) \
@@ -1595,20 +1612,37 @@ static int pick_shape(const CudaEngine *ce, const fsk_b200_geom *g, unsigned nee
 	    if (g->bit_begin[w + 1] != g->bit_begin[w] + N)
 		pf.tiles = 0;
 	pf.nbnd = pf.tiles ? nb + 1u : 2u * nb;
-	pf.bs = 1;
-	while (pf.bs < pf.nbnd)
-	    pf.bs <<= 1;
-	pf.nchunks = (3u + need_floats) / 4u + 1u;
-	/* odd: the 32 lanes of the table build walk their runs in step, cpl float4 apart, and only an odd stride
-	 * spreads a quarter-warp's 16-byte accesses over all banks */
-	pf.cpl = ((pf.nchunks + 31u) / 32u) | 1u;
-	pf.inv_cpl = 1.0f / (float)pf.cpl;
+	/* candidate slots: aligned power-of-two slots reduce by butterflies; slots of exactly nbnd lanes packed
+	 * back to back are used only where they hold more candidates per round (9 boundaries: 3 instead of 2) */
+	unsigned bs2 = 8;
+	int lb = 3;
+	while (bs2 < pf.nbnd) {
+	    bs2 <<= 1;
+	    lb++;
+	}
+	if (pf.nbnd <= 32u && 32u / bs2 == 32u / pf.nbnd) {
+	    pf.bs = bs2;
+	    pf.pow2 = 1;
+	} else {
+	    pf.bs = pf.nbnd;
+	    pf.pow2 = 0;
+	    lb = 1;			/* the kernel's template code for packed slots */
+	}
+	pf.cpr = pf.bs ? 32u / pf.bs : 0u;
+	/* 16-byte pieces of the widest search span (it may start up to 3 samples into its first piece), dealt
+	 * to the 32 lanes in runs of S pieces.  S odd: the lanes walk their runs in step, S pieces apart, and
+	 * only an odd stride spreads a quarter-warp's 16-byte accesses over all banks; the same for the table
+	 * rows (tstride) */
+	const unsigned npieces = (3u + need_floats) / 4u + 1u;
+	pf.S = ((npieces + 31u) / 32u) | 1u;
+	pf.inv_S = 1.0f / (float)pf.S;
+	pf.tstride = ((pf.S + 1u) / 2u) | 1u;
 	const unsigned F = (unsigned)ce->tw_fftsize;
 	const unsigned g4 = (F % 4u == 0) ? 4u : (F % 2u == 0) ? 2u : 1u;
 	pf.fp = F / g4;
 	pf.s4 = 4u / g4;
 	pf.inv_fp = 1.0f / (float)pf.fp;
-	for (unsigned j = 1; j <= 3; j++) {
+	for (unsigned j = 1; j <= 7; j++) {
 	    const double am = 2.0 * M_PI * (double)(((unsigned long long)ce->tw_bm * j) % F) / (double)F;
 	    const double as = 2.0 * M_PI * (double)(((unsigned long long)ce->tw_bs * j) % F) / (double)F;
 	    pf.loc[j - 1][0] = (float)cos(am);
@@ -1616,9 +1650,23 @@ static int pick_shape(const CudaEngine *ce, const fsk_b200_geom *g, unsigned nee
 	    pf.loc[j - 1][2] = (float)cos(as);
 	    pf.loc[j - 1][3] = (float)-sin(as);
 	}
+	for (unsigned k = 0; k < 4; k++) {		/* the rx loop's four searches, src/minimodem.c:1236-1263, :1357-1368 */
+	    const unsigned carrier = k & 1u, fine = k >> 1;
+	    const unsigned tmax_k = carrier ? lc->try_max_carrier : lc->try_max_nocarrier;
+	    const unsigned first = carrier ? lc->nsamples_overscan : 0u;
+	    unsigned step = tmax_k / (fine ? 8u : 3u);
+	    if (step == 0)
+		step = 1;
+	    fsk_b200_pfx_kind &kd = pf.kind[k];
+	    kd.step = step;
+	    kd.k_up = tmax_k > first ? (tmax_k - 1u - first) / step : 0u;
+	    kd.k_dn = first / step < kd.k_up ? first / step : kd.k_up;
+	    kd.ncands = tmax_k > first ? 1u + kd.k_up + kd.k_dn : 0u;
+	}
 	const unsigned ring3 = ce->ring ? ring : ring_min;
-	const size_t table = (size_t)pf.fp * sizeof(float4);
-	const size_t per_stream = (size_t)ring3 * 4 + (size_t)nb * sizeof(float2) + 16 + ((size_t)pf.nchunks + 32u) * sizeof(float4);
+	const unsigned tw_stage = pf.fp + (pf.S + 2u) * pf.s4;	/* one period and a lane-run */
+	const size_t table = (size_t)tw_stage * sizeof(float4);
+	const size_t per_stream = ((size_t)ring3 + 4u * pf.S + 8u) * 4 + (size_t)nb * sizeof(float2) + 16 + (32u * (size_t)pf.tstride + 32u) * sizeof(float4);
 	/* warps (= streams) per block: the most resident streams per SM (each block pays the table and 1 KiB) */
 	const size_t sm_total = (size_t)ce->smem_optin + 1024;
 	int best_wpb = 0;
@@ -1643,11 +1691,12 @@ static int pick_shape(const CudaEngine *ce, const fsk_b200_geom *g, unsigned nee
 	    if (blk <= smem_max)
 		best_wpb = ce->wpb;
 	}
-	if (pf.nbnd <= 32u && best_wpb > 0 && pf.nchunks < 16384u && g->bit_nsamples <= ring3) {
+	if (pf.nbnd <= 32u && best_wpb > 0 && pf.S <= 512u && g->bit_nsamples <= ring3 && ce->twc_n) {
 	    sh->mode = 3;
 	    G = 32;
-	    W = 1;
+	    W = lb;
 	    L = 1;
+	    sh->pfx_tw_stage = tw_stage;
 	    wpb = best_wpb;
 	    ring = ring3;
 	    sh->tw_in_smem = 1;
@@ -1656,7 +1705,7 @@ static int pick_shape(const CudaEngine *ce, const fsk_b200_geom *g, unsigned nee
     }
     /* the table as staged: the window-relative entries, or (per-candidate kernel with the sliding fine
      * search) the absolute-index extension the host layer prepared, if it still fits */
-    sh->geo.tw_entries = sh->mode == 3 ? sh->pfx.fp : g->bit_nsamples;
+    sh->geo.tw_entries = sh->mode == 3 ? sh->pfx_tw_stage : g->bit_nsamples;
     sh->slide = 0;
     if (sh->mode == 0 && lc && lc->slide && g->tw_entries > g->bit_nsamples && sh->tw_in_smem) {
 	const size_t extra = (size_t)(g->tw_entries - g->bit_nsamples) * sizeof(float4);
@@ -1792,8 +1841,9 @@ static int rx_batch_any(CudaEngine *ce, const fsk_b200_geom *g, const fsk_b200_l
 	if (ce->fill != 0)
 	    return -ENOTSUP;
 	if (sh.mode == 3) {
-	    e = launch_rx_t<32, 1, 1, 3, 0, 1>(sh, ce, lc, a, st);
-	    launched = true;
+#define X(WW) if (sh.W == WW) { e = launch_rx_t<32, WW, 1, 3, 0, 1>(sh, ce, lc, a, st); launched = true; }
+	    PFX_SLOTS(X)
+#undef X
 	} else if (sh.mode == 2) {
 #define X(GG, WW, LL) if (sh.G == GG && sh.W == WW && sh.L == LL) { e = launch_rx_t<GG, WW, LL, 2, 0, 1>(sh, ce, lc, a, st); launched = true; }
 	    MULTI_COMBOS(X)
@@ -1809,7 +1859,17 @@ static int rx_batch_any(CudaEngine *ce, const fsk_b200_geom *g, const fsk_b200_l
 	if (!launched)
 	    return -ENOTSUP;
     } else if (sh.mode == 3) {
-	e = launch_rx_t<32, 1, 1, 3, 0>(sh, ce, lc, a, st);
+	/* one stream per warp: the ring is filled by bulk copies of the TMA engine (one elected lane, two to
+	 * four copies per iteration) unless FSK_B200_PFX_FILL=0 asks for the per-lane cp.async fill */
+	if (ce->pfx_fill) {
+#define X(WW) if (sh.W == WW) e = launch_rx_t<32, WW, 1, 3, 1>(sh, ce, lc, a, st);
+	    PFX_SLOTS(X)
+#undef X
+	} else {
+#define X(WW) if (sh.W == WW) e = launch_rx_t<32, WW, 1, 3, 0>(sh, ce, lc, a, st);
+	    PFX_SLOTS(X)
+#undef X
+	}
     } else if (sh.mode == 2) {
 #define X(GG, WW, LL) if (sh.G == GG && sh.W == WW && sh.L == LL) e = launch_rx_t<GG, WW, LL, 2, 0>(sh, ce, lc, a, st);
 	MULTI_COMBOS(X)
@@ -1839,7 +1899,7 @@ static int rx_batch_any(CudaEngine *ce, const fsk_b200_geom *g, const fsk_b200_l
     snprintf(ce->last_kernel, sizeof(ce->last_kernel),
 	    "k_rx<G=%d,W=%d,L=%d,mode=%d(%s),fill=%d,src=%s> threads=%d ring=%u smem=%zu blocks=%d", sh.G, sh.W, sh.L,
 	    sh.mode, sh.mode == 3 ? "prefix-table" : sh.mode == 2 ? "shared-segment" : sh.mode == 0 ? "per-candidate" : "generic",
-	    sh.mode == 0 ? ce->fill : 0, elem == 2 ? (sh.slide ? "s16,slide" : "s16") : (sh.slide ? "f32,slide" : "f32"),
+	    sh.mode == 0 ? ce->fill : (sh.mode == 3 && elem == 4) ? ce->pfx_fill : 0, elem == 2 ? (sh.slide ? "s16,slide" : "s16") : (sh.slide ? "f32,slide" : "f32"),
 	    sh.wpb * 32, sh.ring, sh.smem, sh.blocks);
     if (e != cudaSuccess) {
 	fsk_b200_set_error("rx_batch launch (G=%d W=%d L=%d mode=%d ring=%u smem=%zu): %s", sh.G, sh.W,

@@ -1164,7 +1164,8 @@ def test_baseline_configs_large_batch_sample_vs_oracle(mode, kw, nstreams, nword
     frames, states = eng.rx_batch(x, nsamples=n)
     torch.cuda.synchronize()
     # the default policy: shared-segment search where the bit period is long and the windows tile
-    assert ("shared-segment" in eng.last_kernel()) == (mode in ("rtty", "300")), eng.last_kernel()
+    if not (os.environ.get("FSK_B200_PREFIX") or os.environ.get("FSK_B200_MULTI")):      # the defaults, unless a run forces a variant
+        assert ("shared-segment" in eng.last_kernel() or "prefix-table" in eng.last_kernel()) == (mode in ("rtty", "300")), eng.last_kernel()
     st = mm.states_to_numpy(states)
     assert (st["done"] == 1).all()
     rows = np.arange(0, nstreams, max(1, nstreams // max(8, nstreams // 100)))
