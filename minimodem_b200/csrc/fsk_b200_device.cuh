@@ -1123,23 +1123,56 @@ __device__ __forceinline__ PfxLane pfx_lane(const fsk_b200_geom &geo, const fsk_
     return pl;
 }
 
-/* the chunk-local twiddles exp(-2 pi i b j / fftsize), j = 1..7, held in registers for the table build */
-struct PfxLoc {
-    float v[7][4];
+/* Two fp32 multiply-adds in one instruction (Blackwell FFMA2: fma.rn.f32x2 on 64-bit register pairs).  The
+ * table build is bound by instruction issue, not by the FMA pipe, so halving the instruction count of its
+ * inner sums is worth more than the pipe cycles. */
+struct F2 {
+    float lo, hi;
 };
-/* eight samples against both tones, phase counted from the first: (re, im) mark, (re, im) space */
+#ifndef FSK_EMU	/* inline PTX: the host emulation of the test harness brings its own */
+__device__ __forceinline__ F2 fma2(const F2 a, const F2 b, const F2 c)
+{
+    unsigned long long ua, ub, uc, ud;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ua) : "f"(a.lo), "f"(a.hi));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ub) : "f"(b.lo), "f"(b.hi));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(uc) : "f"(c.lo), "f"(c.hi));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(ud) : "l"(ua), "l"(ub), "l"(uc));
+    F2 d;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.lo), "=f"(d.hi) : "l"(ud));
+    return d;
+}
+__device__ __forceinline__ F2 mul2(const F2 a, const F2 b)
+{
+    unsigned long long ua, ub, ud;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ua) : "f"(a.lo), "f"(a.hi));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ub) : "f"(b.lo), "f"(b.hi));
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(ud) : "l"(ua), "l"(ub));
+    F2 d;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.lo), "=f"(d.hi) : "l"(ud));
+    return d;
+}
+#else		/* host emulation (tests/emu): the two halves one after the other, each with one rounding */
+static inline F2 fma2(const F2 a, const F2 b, const F2 c) { return F2{ fmaf(a.lo, b.lo, c.lo), fmaf(a.hi, b.hi, c.hi) }; }
+static inline F2 mul2(const F2 a, const F2 b) { return F2{ a.lo * b.lo, a.hi * b.hi }; }
+#endif
+
+/* eight samples against both tones, phase counted from the first: (re, im) mark, (re, im) space.
+ * loc[p][k] = the twiddles exp(-2 pi i b j / fftsize) of the sample pair j = 2p, 2p + 1, component
+ * k = (re, im) mark, (re, im) space (j = 0: 1, 0, 1, 0), side by side as FFMA2 wants them.
+ * Even and odd samples are summed side by side and added at the end. */
 template <class LOC>
 __device__ __forceinline__ float4 pfx_local(const float4 a, const float4 b, const LOC &loc)
 {
     float4 s;
-    s.x = fmaf(b.w, loc[6][0], fmaf(b.z, loc[5][0], fmaf(b.y, loc[4][0], fmaf(b.x, loc[3][0],
-	    fmaf(a.w, loc[2][0], fmaf(a.z, loc[1][0], fmaf(a.y, loc[0][0], a.x)))))));
-    s.y = fmaf(b.w, loc[6][1], fmaf(b.z, loc[5][1], fmaf(b.y, loc[4][1], fmaf(b.x, loc[3][1],
-	    fmaf(a.w, loc[2][1], fmaf(a.z, loc[1][1], a.y * loc[0][1]))))));
-    s.z = fmaf(b.w, loc[6][2], fmaf(b.z, loc[5][2], fmaf(b.y, loc[4][2], fmaf(b.x, loc[3][2],
-	    fmaf(a.w, loc[2][2], fmaf(a.z, loc[1][2], fmaf(a.y, loc[0][2], a.x)))))));
-    s.w = fmaf(b.w, loc[6][3], fmaf(b.z, loc[5][3], fmaf(b.y, loc[4][3], fmaf(b.x, loc[3][3],
-	    fmaf(a.w, loc[2][3], fmaf(a.z, loc[1][3], a.y * loc[0][3]))))));
+    float *sp = &s.x;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+	F2 acc = mul2(F2{ a.x, a.y }, F2{ loc[0][k][0], loc[0][k][1] });
+	acc = fma2(F2{ a.z, a.w }, F2{ loc[1][k][0], loc[1][k][1] }, acc);
+	acc = fma2(F2{ b.x, b.y }, F2{ loc[2][k][0], loc[2][k][1] }, acc);
+	acc = fma2(F2{ b.z, b.w }, F2{ loc[3][k][0], loc[3][k][1] }, acc);
+	sp[k] = acc.lo + acc.hi;
+    }
     return s;
 }
 /* the same for a single piece (the last chunk of a run) */
@@ -1147,10 +1180,13 @@ template <class LOC>
 __device__ __forceinline__ float4 pfx_local4(const float4 a, const LOC &loc)
 {
     float4 s;
-    s.x = fmaf(a.w, loc[2][0], fmaf(a.z, loc[1][0], fmaf(a.y, loc[0][0], a.x)));
-    s.y = fmaf(a.w, loc[2][1], fmaf(a.z, loc[1][1], a.y * loc[0][1]));
-    s.z = fmaf(a.w, loc[2][2], fmaf(a.z, loc[1][2], fmaf(a.y, loc[0][2], a.x)));
-    s.w = fmaf(a.w, loc[2][3], fmaf(a.z, loc[1][3], a.y * loc[0][3]));
+    float *sp = &s.x;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+	F2 acc = mul2(F2{ a.x, a.y }, F2{ loc[0][k][0], loc[0][k][1] });
+	acc = fma2(F2{ a.z, a.w }, F2{ loc[1][k][0], loc[1][k][1] }, acc);
+	sp[k] = acc.lo + acc.hi;
+    }
     return s;
 }
 /* acc += rot * s, tone by tone (complex) */
@@ -1169,7 +1205,8 @@ __device__ __forceinline__ void pfx_rot_acc(float4 &acc, const float4 rt, const 
  * is mirrored behind its end for the length of a run and the rotation table is staged a run longer than
  * its period, so a run is three linear walks: no wrap tests. */
 __device__ __forceinline__ void pfx_build(const float *ring, unsigned R, unsigned base, unsigned npieces,
-	float4 *pre, float4 *tot, const float4 *twc, const fsk_b200_pfx &pg, const PfxLane &pl, unsigned lane)
+	float4 *pre, float4 *tot, const float4 *twc, const float4 *loc_s, const fsk_b200_pfx &pg, const PfxLane &pl,
+	unsigned lane)
 {
     const unsigned S = pg.S, q0 = lane * S;
     const unsigned avail = q0 < npieces ? min(S, npieces - q0) : 0u;	/* pieces of this run that are needed */
@@ -1181,19 +1218,29 @@ __device__ __forceinline__ void pfx_build(const float *ring, unsigned R, unsigne
     const float4 *tp = twc + pl.idx0;
     const unsigned step2 = 2u * pg.s4;
     float4 *row = pre + lane * pg.tstride;
-    PfxLoc lc;
+    /* the chunk-local twiddles in (vector) registers for the walk: as kernel parameters the compiler keeps
+     * them in uniform registers and then spends more instructions pairing those up for FFMA2 than the sums
+     * take; loaded from the block's shared copy through an address it cannot prove uniform, they are
+     * ordinary register pairs */
+    float lc[4][4][2];
+    {
+	const float4 *lp = loc_s + (lane & pg.zero);
 #pragma unroll
-    for (int j = 0; j < 7; j++)
+	for (int p = 0; p < 4; p++)
 #pragma unroll
-	for (int k = 0; k < 4; k++)
-	    lc.v[j][k] = pg.loc[j][k];
+	    for (int k2 = 0; k2 < 2; k2++) {
+		const float4 v = lp[p * 2 + k2];
+		lc[p][2 * k2][0] = v.x; lc[p][2 * k2][1] = v.y;
+		lc[p][2 * k2 + 1][0] = v.z; lc[p][2 * k2 + 1][1] = v.w;
+	    }
+    }
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 4
     for (unsigned c = 0; c < nfull; c++) {
 	const float4 xa = xp[0], xb = xp[1];
 	const float4 rt = *tp;
 	row[c] = acc;
-	pfx_rot_acc(acc, rt, pfx_local(xa, xb, lc.v));
+	pfx_rot_acc(acc, rt, pfx_local(xa, xb, lc));
 	xp += 2;
 	tp += step2;
     }
@@ -1201,7 +1248,7 @@ __device__ __forceinline__ void pfx_build(const float *ring, unsigned R, unsigne
 	const float4 xa = xp[0];
 	const float4 rt = *tp;
 	row[nfull] = acc;
-	pfx_rot_acc(acc, rt, pfx_local4(xa, lc.v));
+	pfx_rot_acc(acc, rt, pfx_local4(xa, lc));
     }
     tot[lane] = acc;
 }
@@ -1296,7 +1343,8 @@ __device__ __forceinline__ float pfx_round(const float *ring, unsigned R, unsign
     const unsigned l_e = __shfl_sync(FULL, l_b, pl.peer);
     const bool own = pl.win && valid;
     if (own) {
-	for (unsigned l = l_b; l < l_e; l++) {		/* the lane-runs the window crosses */
+#pragma unroll 1
+	for (unsigned l = l_b; l < l_e; l++) {		/* the lane-runs the window crosses: a few */
 	    const float4 tl = tot[l];
 	    S.x += tl.x; S.y += tl.y; S.z += tl.z; S.w += tl.w;
 	}
@@ -1419,11 +1467,9 @@ __device__ __forceinline__ Found pfx_search(const float *ring, unsigned R, unsig
 	if (reach)
 	    src = (unsigned)__ffs((int)reach) - 1u;
 	else {
-	    float cm = c;
-#pragma unroll
-	    for (unsigned d = 16u; d; d >>= 1)
-		cm = fmaxf(cm, __shfl_xor_sync(FULL, cm, d));
-	    src = (unsigned)__ffs((int)__ballot_sync(FULL, c == cm)) - 1u;
+	    /* (c >= 0: floats order like their bit patterns; one REDUX instead of a five-stage butterfly) */
+	    const unsigned cm = __reduce_max_sync(FULL, __float_as_uint(c));
+	    src = (unsigned)__ffs((int)__ballot_sync(FULL, __float_as_uint(c) == cm)) - 1u;
 	}
 	const float cw = __shfl_sync(FULL, c, src);
 	if (best.confidence < cw) {

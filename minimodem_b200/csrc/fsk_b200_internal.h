@@ -103,8 +103,9 @@ typedef struct fsk_b200_pfx {
     uint32_t	tstride;	/* table entries per lane-run: (S + 1) / 2 chunks, made odd */
     uint32_t	fp, s4;		/* the piece at index q is rotated by table entry (s4 * q) mod fp: fp = fftsize / gcd(4, fftsize), s4 = 4 / gcd */
     float	inv_fp;
-    float	loc[7][4];	/* exp(-2 pi i b j / fftsize), j = 1..7, as (re, im) for b_mark, b_space: the samples of a chunk */
+    float	loc[4][4][2];	/* [p][k][h]: exp(-2 pi i b j / fftsize) for sample j = 2p + h of a chunk, k = (re, im) of b_mark, (re, im) of b_space */
     fsk_b200_pfx_kind kind[4];	/* [carrier + 2 * fine], as fsk_b200_mplan.kind */
+    uint32_t	zero;		/* 0 (an operand the compiler cannot see through) */
 } fsk_b200_pfx;
 
 void fsk_b200_set_error(const char *fmt, ...);

@@ -67,6 +67,7 @@ struct Smem {
     float2 *scr;
     unsigned long long *bars;	/* two mbarriers per stream (bulk fill) */
     float4 *pre, *tot;		/* MODE 3: the stream's chunk-prefix table and its 32 lane-run totals */
+    const float4 *loc;		/* MODE 3: the block's copy of fsk_b200_pfx.loc (8 float4) */
 };
 
 /* pad: floats of the ring's head mirrored behind its end (0: no mirror); pfx_chunks: MODE 3 table entries
@@ -74,7 +75,7 @@ struct Smem {
 template <int G>
 __device__ __forceinline__ Smem carve(float4 *smem, const fsk_b200_geom &geo,
 	const float4 *__restrict__ tw_global, unsigned tw_in_smem, unsigned ring_floats, unsigned pad,
-	unsigned pfx_chunks = 0)
+	unsigned pfx_chunks = 0, const float *pfx_loc = nullptr)
 {
     const unsigned N = geo.tw_entries, wpb = blockDim.x >> 5;	/* table entries staged (>= bit_nsamples) */
     Smem s;
@@ -99,6 +100,12 @@ __device__ __forceinline__ Smem carve(float4 *smem, const fsk_b200_geom &geo,
     unsigned long long *bars = reinterpret_cast<unsigned long long *>(scrs + (((size_t)wpb * spw * geo.n_bits + 1u) & ~(size_t)1u));
     s.bars = bars + 2 * slot;
     float4 *pfx = reinterpret_cast<float4 *>(bars + 2 * (size_t)wpb * spw);
+    s.loc = pfx;
+    if (pfx_chunks) {
+	if (threadIdx.x < 32u)
+	    reinterpret_cast<float *>(pfx)[threadIdx.x] = pfx_loc[threadIdx.x];
+	pfx += 8;
+    }
     s.pre = pfx + (size_t)slot * (pfx_chunks + 32u);
     s.tot = s.pre + pfx_chunks;
     __syncthreads();
@@ -251,7 +258,8 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
      * (tw_sample) */
     const unsigned ring_pad = MODE == 3 ? 4u * pg.S + 8u : (geo.bit_nsamples + 3u) & ~3u;
     constexpr int LB = W == 1 ? 0 : W;		/* MODE 3: log2 of the candidate slot (0: packed slots of any size) */
-    const Smem sm = carve<G>(smem4, geo, tw_global, tw_in_smem, ring_floats, ring_pad, MODE == 3 ? 32u * pg.tstride : 0u);
+    const Smem sm = carve<G>(smem4, geo, tw_global, tw_in_smem, ring_floats, ring_pad, MODE == 3 ? 32u * pg.tstride : 0u,
+	    &pg.loc[0][0][0]);
     GROUP_VARS;
     const Ring rg = { smem_u32(sm.ring), ring_floats, ring_pad };
     const unsigned tw_s = tw_in_smem ? smem_u32(sm.tw) : 0u;	/* the fast path requires the table in shared memory */
@@ -259,7 +267,7 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
     const LaneWin<W> lw = lane_windows<G, W, L>(geo, g);
     const LaneWinM<W> lwm = lane_windows_multi<G, W, L>(geo, g);
     const PfxLane pfl = MODE == 3 ? pfx_lane(geo, pg, lane) : PfxLane();
-    const unsigned pre_s = smem_u32(sm.pre), tot_s = smem_u32(sm.tot);
+    const unsigned pre_s = smem_u32(sm.pre), tot_s = smem_u32(sm.tot), loc_s = smem_u32(sm.loc);
     const unsigned R = ring_floats;
 
     for (unsigned s = (blockIdx.x * wpb + warp) * spw + sidx; s < a.nstreams;
@@ -479,6 +487,7 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
 			float4 *pre = static_cast<float4 *>(__cvta_shared_to_generic(pre_s));
 			float4 *tot = static_cast<float4 *>(__cvta_shared_to_generic(tot_s));
 			const float4 *twc = static_cast<const float4 *>(__cvta_shared_to_generic(tw_s));
+			const float4 *locp = static_cast<const float4 *>(__cvta_shared_to_generic(loc_s));
 			const unsigned base = pos_off & ~3u;
 			if (pass == 0) {
 			    if (pending) {
@@ -487,7 +496,7 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
 				pending = false;
 			    }
 			    pfx_build(ringp, R, base, ((pos_off & 3u) + try_max - 1u + geo.span) / 4u + 1u, pre, tot,
-				    twc, pg, pfl, lane);
+				    twc, locp, pg, pfl, lane);
 			    __syncwarp(gmask);
 			}
 			f = pfx_search<LB>(ringp, R, base, pos_off & 3u, pre, tot, twc, tw_sample, pg, geo, pfl, which,
@@ -1316,7 +1325,8 @@ extern "C" int fsk_b200_cuda_tune(void *p, int lanes, int wpb, int ring)
 #define FSK_PFX_MAX_TABLE_BYTES (16u * 1024u)
 #define FSK_PFX_TABLE_EXTRA 2056u	/* rotation-table entries past one period (a lane-run of up to 512 pieces, s4 <= 4) */
 #ifndef FSK_PREFIX_MIN_N
-#define FSK_PREFIX_MIN_N 170u	/* shortest bit period (samples) for which mode 3 is the default (measured: RTTY @8 kHz, 176) */
+#define FSK_PREFIX_MIN_N 128u	/* shortest bit period (samples) for which mode 3 is the default: measured faster than the shared
+				 * segments at 160 (Bell103) and 176 (RTTY @8 kHz), slower than the per-candidate kernel at 92 (SAME) and 40 */
 #endif
 
 /* exp(-2 pi i k n / fftsize) for k = b_mark, b_space; the argument is reduced
@@ -1642,13 +1652,13 @@ static int pick_shape(const CudaEngine *ce, const fsk_b200_geom *g, unsigned nee
 	pf.fp = F / g4;
 	pf.s4 = 4u / g4;
 	pf.inv_fp = 1.0f / (float)pf.fp;
-	for (unsigned j = 1; j <= 7; j++) {
+	for (unsigned j = 0; j <= 7; j++) {
 	    const double am = 2.0 * M_PI * (double)(((unsigned long long)ce->tw_bm * j) % F) / (double)F;
 	    const double as = 2.0 * M_PI * (double)(((unsigned long long)ce->tw_bs * j) % F) / (double)F;
-	    pf.loc[j - 1][0] = (float)cos(am);
-	    pf.loc[j - 1][1] = (float)-sin(am);
-	    pf.loc[j - 1][2] = (float)cos(as);
-	    pf.loc[j - 1][3] = (float)-sin(as);
+	    pf.loc[j >> 1][0][j & 1u] = j ? (float)cos(am) : 1.0f;
+	    pf.loc[j >> 1][1][j & 1u] = j ? (float)-sin(am) : 0.0f;
+	    pf.loc[j >> 1][2][j & 1u] = j ? (float)cos(as) : 1.0f;
+	    pf.loc[j >> 1][3][j & 1u] = j ? (float)-sin(as) : 0.0f;
 	}
 	for (unsigned k = 0; k < 4; k++) {		/* the rx loop's four searches, src/minimodem.c:1236-1263, :1357-1368 */
 	    const unsigned carrier = k & 1u, fine = k >> 1;
@@ -1672,7 +1682,7 @@ static int pick_shape(const CudaEngine *ce, const fsk_b200_geom *g, unsigned nee
 	int best_wpb = 0;
 	size_t best_streams = 0;
 	for (int w = 1; w <= FSK_PFX_MAXTHREADS / 32; w++) {
-	    const size_t blk = ((table + (size_t)w * per_stream + 16 + 15) & ~(size_t)15);
+	    const size_t blk = ((table + (size_t)w * per_stream + 16 + 128 + 15) & ~(size_t)15);
 	    if (blk > smem_max)
 		break;
 	    size_t nblk = sm_total / (blk + 1024);
@@ -1687,7 +1697,7 @@ static int pick_shape(const CudaEngine *ce, const fsk_b200_geom *g, unsigned nee
 	    }
 	}
 	if (ce->wpb && ce->prefix > 0) {
-	    const size_t blk = ((table + (size_t)ce->wpb * per_stream + 16 + 15) & ~(size_t)15);
+	    const size_t blk = ((table + (size_t)ce->wpb * per_stream + 16 + 128 + 15) & ~(size_t)15);
 	    if (blk <= smem_max)
 		best_wpb = ce->wpb;
 	}
@@ -1700,7 +1710,7 @@ static int pick_shape(const CudaEngine *ce, const fsk_b200_geom *g, unsigned nee
 	    wpb = best_wpb;
 	    ring = ring3;
 	    sh->tw_in_smem = 1;
-	    sh->smem = ((table + (size_t)wpb * per_stream + 16 + 15) & ~(size_t)15);
+	    sh->smem = ((table + (size_t)wpb * per_stream + 16 + 128 + 15) & ~(size_t)15);
 	}
     }
     /* the table as staged: the window-relative entries, or (per-candidate kernel with the sliding fine

@@ -210,6 +210,21 @@ static inline unsigned ballot(unsigned mask, int pred)
     return r;
 }
 
+/* __reduce_max_sync (redux.sync.max.u32): the largest value among the lanes of the mask */
+static inline unsigned reduce_max(unsigned mask, unsigned v)
+{
+    Block *b = blk;
+    b->xchg[b->cur] = v;
+    rendezvous(mask);
+    unsigned r = 0;
+    const unsigned base = b->cur & ~31u;
+    for (unsigned l = 0; l < 32u && base + l < b->bdim.x; l++)
+	if ((mask >> l & 1u) && (unsigned)b->xchg[base + l] > r)
+	    r = (unsigned)b->xchg[base + l];
+    rendezvous(mask);
+    return r;
+}
+
 /* cp.async */
 static inline void land(const Pending &p)
 {
@@ -288,6 +303,7 @@ template <class T>
 static inline T __shfl_sync(unsigned mask, T v, int src_lane, int width = 32) { return emu::shfl_idx(mask, v, src_lane, width); }
 static inline int __any_sync(unsigned mask, int pred) { return emu::ballot(mask, pred) != 0u; }
 static inline unsigned __ballot_sync(unsigned mask, int pred) { return emu::ballot(mask, pred); }
+static inline unsigned __reduce_max_sync(unsigned mask, unsigned v) { return emu::reduce_max(mask, v); }
 static inline int __ffs(int v) { return __builtin_ffs(v); }
 static inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
 template <class T>

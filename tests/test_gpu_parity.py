@@ -7,6 +7,7 @@ Bars: bits / frame_start / decoded bytes bit-exact; confidence and amplitude
 within 1e-4 relative (+ the conditioning term of golden_util.close for
 confidences >> 1, where two correct FFTs already disagree); inf is a class."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
