@@ -1798,6 +1798,8 @@ __device__ __forceinline__ void ring_zero(const Ring rg, unsigned pos, unsigned 
 	unsigned off = (unsigned)off0;
 	if (off >= rg.R)
 	    off -= rg.R;
+	if (off >= rg.R)		/* (an early request for the NEXT window reaches up to two ring lengths ahead of pos) */
+	    off -= rg.R;
 	float *ring = static_cast<float *>(__cvta_shared_to_generic(rg.ring_s));
 	ring[off] = 0.f;
 	if (off < rg.pad)

@@ -581,6 +581,9 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
 			__syncwarp(gmask);	/* every read of this window precedes the copies */
 			request_at(min((npos + lookahead + need_max + 3u) & ~3u, (npos & ~AL) + R), npos);
 		    }
+		    /* (The bulk fill of MODE 3 asks at the top of the next iteration.  Asking here as well --
+		     * one more barrier phase per iteration, measured -- is 4 % slower: the state machine below
+		     * is too short to hide a copy, and the other warps of the SM do that already.) */
 		}
 	    } else if (SRC)
 		confidence = find_frame<G, GlobalSrc16>(gsrc16, pos, geo, sel, sm.tw, sm.scr, g, gmask,

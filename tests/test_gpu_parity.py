@@ -1132,6 +1132,61 @@ def test_rx_kernel_variants_agree_with_the_oracle(name, variant, monkeypatch):
 
 
 # --------------------------------------------------------------------------
+# the prefix-table kernel against the per-candidate kernel, frame by frame, far inside the oracle tolerance:
+# the two form every window sum in a different order (chunk prefixes and their differences against one
+# direct sum per window), so this is the per-window arithmetic of the new kernel checked to a few 1e-6 on
+# noisy, offset and clean streams, the orthogonal-tone geometry (confidence = inf class) included
+# --------------------------------------------------------------------------
+@pytest.mark.parametrize("mode,kw,sigma", [
+    ("300", {}, 0.0), ("300", {}, 0.2), ("rtty", dict(sample_rate=8000), 0.1), ("1200", {}, 0.3),
+    ("same", {}, 0.05), ("1200", dict(mark=1200, space=2400), 0.0), ("300", dict(stopbits=2.0, startbits=2), 0.1)],
+    ids=["bell103", "bell103-awgn", "rtty8k-awgn", "1200-awgn", "same-awgn", "orthogonal-tones", "300-2start-2stop"])
+def test_prefix_table_kernel_against_the_per_candidate_kernel(mode, kw, sigma, monkeypatch):
+    rx = orc.Mode(mode, **kw)
+    d = rx.derived()
+    rng = np.random.default_rng(77)
+    streams = []
+    for s in range(24):
+        w = rng.integers(0, 1 << rx.n_data_bits, int(rng.integers(6, 30)), dtype=np.uint64).astype(np.uint32)
+        x = np.concatenate([np.zeros(int(rng.integers(0, 4 * int(d.nsamples_per_bit))), np.float32),
+                            orc.tx_words(rx, w, float(rng.uniform(0.2, 1.0)), 4096, True)]).astype(np.float32)
+        if sigma:
+            x = (x + np.float32(sigma * (0.5 + rng.random())) * rng.standard_normal(x.size).astype(np.float32)).astype(np.float32)
+        if s % 5 == 4:
+            x = (x - np.float32(0.07)).astype(np.float32)          # the reference's --Xrxnoise style offset
+        streams.append(x)
+    res = {}
+    for variant, env in (("prefix", {"FSK_B200_PREFIX": "1"}), ("per-candidate", {"FSK_B200_PREFIX": "0", "FSK_B200_MULTI": "0"})):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        eng, _ = engine_for((mode, kw))
+        res[variant] = rx_on_gpu(eng, streams)
+        assert ("prefix-table" in eng.last_kernel()) == (variant == "prefix"), eng.last_kernel()
+        for k in env:
+            monkeypatch.delenv(k)
+    nframes = n_inf = 0
+    for s in range(len(streams)):
+        a, b = res["prefix"][0][s], res["per-candidate"][0][s]
+        assert len(a) == len(b), (mode, s, len(a), len(b))
+        for key in ("bits_lo", "bits_hi", "frame_start"):
+            assert np.array_equal(a[key], b[key]), (mode, s, key)
+        ca, cb = a["confidence"].astype(np.float64), b["confidence"].astype(np.float64)
+        rep = a["frame_start"] == mm.FRAME_REPORT                    # (session reports carry sums, not confidences)
+        inf = np.isinf(cb) & ~rep
+        assert np.array_equal(np.isinf(ca) & ~rep, inf), (mode, s)
+        fin = ~inf
+        # a confidence is signal / noise: its sensitivity to the sums is ~confidence itself
+        assert np.all(np.abs(ca[fin] - cb[fin]) <= 4e-6 * np.maximum(1.0, np.abs(cb[fin])) * np.abs(cb[fin]) + 1e-6), \
+            (mode, s, float(np.max(np.abs(ca[fin] - cb[fin]) / np.maximum(np.abs(cb[fin]), 1e-9))))
+        assert np.allclose(a["amplitude"], b["amplitude"], rtol=4e-6, atol=1e-7), (mode, s)
+        nframes += int((~rep).sum())
+        n_inf += int(inf.sum())
+    assert nframes > 200, nframes
+    if kw.get("space") == 2400 and not sigma:
+        assert n_inf > 0
+
+
+# --------------------------------------------------------------------------
 # the BASELINE configurations at batch sizes of the bench's order (>= 16 384 streams each), generated
 # on the device, a 1 % sample of the streams compared with the oracle frame by frame
 # --------------------------------------------------------------------------
