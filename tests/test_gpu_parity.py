@@ -1095,10 +1095,11 @@ def test_per_bit_magnitudes_vs_oracle(mode, kw):
 # (cp.async.bulk + mbarrier, FILL=1) and the warp-synchronous loop (FILL=3), each against the
 # oracle on the same streams
 # --------------------------------------------------------------------------
-@pytest.mark.parametrize("variant", ["prefix", "multi", "multi-hybrid", "per-candidate", "tma-bulk", "warp-sync"])
+@pytest.mark.parametrize("variant", ["prefix", "prefix-cpasync", "multi", "multi-hybrid", "per-candidate", "tma-bulk", "warp-sync"])
 @pytest.mark.parametrize("name", ["01-self-test-1200", "02-self-test-300", "small-rtty"])
 def test_rx_kernel_variants_agree_with_the_oracle(name, variant, monkeypatch):
     env = {"prefix": {"FSK_B200_PREFIX": "1"},
+           "prefix-cpasync": {"FSK_B200_PREFIX": "1", "FSK_B200_PFX_FILL": "0"},      # (what int16 rows and the emulator run)
            "multi": {"FSK_B200_MULTI": "2", "FSK_B200_PREFIX": "0"},
            "multi-hybrid": {"FSK_B200_MULTI": "1", "FSK_B200_PREFIX": "0"},
            "per-candidate": {"FSK_B200_MULTI": "0", "FSK_B200_PREFIX": "0"},
@@ -1118,8 +1119,8 @@ def test_rx_kernel_variants_agree_with_the_oracle(name, variant, monkeypatch):
     streams.append((a + 0.05 * rng.standard_normal(a.size)).astype(np.float32))
     recs, st = rx_on_gpu(eng, streams)
     kern = eng.last_kernel()
-    if variant == "prefix":
-        assert "prefix-table" in kern, kern
+    if variant.startswith("prefix"):
+        assert "prefix-table" in kern and ("fill=0" in kern) == (variant == "prefix-cpasync" or conftest.EMU_DEVICE is not None), kern
     elif variant.startswith("multi"):
         assert "shared-segment" in kern, kern
     elif variant == "per-candidate":
