@@ -1105,8 +1105,8 @@ __device__ __forceinline__ PfxLane pfx_lane(const fsk_b200_geom &geo, const fsk_
     const unsigned nb = geo.n_bits, N = geo.bit_nsamples;
     pl.cslot = min(lane / pg.bs, pg.cpr);
     pl.kk = lane - pl.cslot * pg.bs;
-    pl.sbase = pl.cslot * pg.bs;
     const bool in_slot = pl.cslot < pg.cpr;
+    pl.sbase = in_slot ? pl.cslot * pg.bs : 0u;		/* (an idle lane adds up slot 0: sbase + bs stays inside the scratch) */
     pl.win = in_slot && pl.kk < nb;
     if (pl.win)
 	pl.bb = geo.bit_begin[pl.kk];
@@ -1254,10 +1254,13 @@ __device__ __forceinline__ void pfx_build(const float *ring, unsigned R, unsigne
 }
 
 /* Sums over the lanes of a candidate slot; every lane of the slot ends with the total.  LB > 0: the slot is
- * 1 << LB lanes, aligned (butterfly); LB == 0: any slot size (pg.bs), packed back to back. */
+ * 1 << LB lanes, aligned: butterflies.  LB == 0: slots of any size (pg.bs) packed back to back; a shuffle
+ * tree over such a slot needs a source clamp, a bounds test and a select per value and step (measured at
+ * RTTY: a quarter of all instructions), so the lanes leave their terms in the stream's 32-entry scratch
+ * `red` and every lane adds up its slot's entries in lane order: 1 store + bs broadcast loads. */
 template <int LB>
 __device__ __forceinline__ void pfx_slot_sum4(float &a, float &b, float &c, unsigned &d, const fsk_b200_pfx &pg,
-	const PfxLane &pl, unsigned lane)
+	const PfxLane &pl, unsigned lane, float4 *red)
 {
     const unsigned FULL = 0xffffffffu;
     if (LB > 0) {
@@ -1269,24 +1272,24 @@ __device__ __forceinline__ void pfx_slot_sum4(float &a, float &b, float &c, unsi
 	    d += __shfl_xor_sync(FULL, d, o);
 	}
     } else {
-	for (unsigned o = 1; o < pg.bs; o <<= 1) {
-	    const unsigned src = min(lane + o, 31u);
-	    const bool ok = pl.kk + o < pg.bs;
-	    const float a2 = __shfl_sync(FULL, a, src), b2 = __shfl_sync(FULL, b, src), c2 = __shfl_sync(FULL, c, src);
-	    const unsigned d2 = __shfl_sync(FULL, d, src);
-	    a += ok ? a2 : 0.f;
-	    b += ok ? b2 : 0.f;
-	    c += ok ? c2 : 0.f;
-	    d += ok ? d2 : 0u;
+	red[lane] = make_float4(a, b, c, __uint_as_float(d));
+	__syncwarp();
+	const float4 *rp = red + pl.sbase;
+	a = b = c = 0.f;
+	d = 0u;
+	for (unsigned k = 0; k < pg.bs; k++) {
+	    const float4 v = rp[k];
+	    a += v.x;
+	    b += v.y;
+	    c += v.z;
+	    d += __float_as_uint(v.w);
 	}
-	a = __shfl_sync(FULL, a, pl.sbase);
-	b = __shfl_sync(FULL, b, pl.sbase);
-	c = __shfl_sync(FULL, c, pl.sbase);
-	d = __shfl_sync(FULL, d, pl.sbase);
+	__syncwarp();			/* the scratch is written again right away (pfx_slot_sum1) */
     }
 }
 template <int LB>
-__device__ __forceinline__ float pfx_slot_sum1(float a, const fsk_b200_pfx &pg, const PfxLane &pl, unsigned lane)
+__device__ __forceinline__ float pfx_slot_sum1(float a, const fsk_b200_pfx &pg, const PfxLane &pl, unsigned lane,
+	float4 *red)
 {
     const unsigned FULL = 0xffffffffu;
     if (LB > 0) {
@@ -1295,11 +1298,15 @@ __device__ __forceinline__ float pfx_slot_sum1(float a, const fsk_b200_pfx &pg, 
 	    a += __shfl_xor_sync(FULL, a, o);
 	return a;
     }
-    for (unsigned o = 1; o < pg.bs; o <<= 1) {
-	const float a2 = __shfl_sync(FULL, a, min(lane + o, 31u));
-	a += pl.kk + o < pg.bs ? a2 : 0.f;
-    }
-    return __shfl_sync(FULL, a, pl.sbase);
+    float *rf = reinterpret_cast<float *>(red);
+    rf[lane] = a;
+    __syncwarp();
+    const float *rp = rf + pl.sbase;
+    a = 0.f;
+    for (unsigned k = 0; k < pg.bs; k++)
+	a += rp[k];
+    __syncwarp();
+    return a;
 }
 
 /* One round: the candidates `t` of the cpr slots (valid or not, per slot), every window of every one
@@ -1308,7 +1315,7 @@ __device__ __forceinline__ float pfx_slot_sum1(float a, const fsk_b200_pfx &pg, 
 template <int LB>
 __device__ __forceinline__ float pfx_round(const float *ring, unsigned R, unsigned base, unsigned r0, unsigned t,
 	bool valid, const float4 *pre, const float4 *tot, const float4 *twc, const float4 *__restrict__ tw_sample,
-	const fsk_b200_pfx &pg, const fsk_b200_geom &geo, const PfxLane &pl, int sel, unsigned lane,
+	const fsk_b200_pfx &pg, const fsk_b200_geom &geo, const PfxLane &pl, int sel, unsigned lane, float4 *red,
 	unsigned &bits_lo_out, unsigned &bits_hi_out, float &ampl_out, float2 *bit_mags = nullptr)
 {
     const unsigned FULL = 0xffffffffu;
@@ -1393,16 +1400,16 @@ __device__ __forceinline__ float pfx_round(const float *ring, unsigned R, unsign
      * (disjoint bit positions: OR == ADD) when the frame is short enough */
     if (nb <= 24u) {
 	unsigned packed = blo | (mark ? 1u << 24 : 0u);
-	pfx_slot_sum4<LB>(tn, am, as, packed, pg, pl, lane);
+	pfx_slot_sum4<LB>(tn, am, as, packed, pg, pl, lane, red);
 	blo = packed & 0xffffffu;
 	nm = packed >> 24;
     } else {
 	float z0 = 0.f, z1 = 0.f, z2 = 0.f;
 	nm = mark ? 1u : 0u;
-	pfx_slot_sum4<LB>(tn, am, as, nm, pg, pl, lane);
+	pfx_slot_sum4<LB>(tn, am, as, nm, pg, pl, lane, red);
 	/* bit positions are disjoint, so the words add like they OR */
-	pfx_slot_sum4<LB>(z0, z1, z2, blo, pg, pl, lane);
-	pfx_slot_sum4<LB>(z0, z1, z2, bhi, pg, pl, lane);
+	pfx_slot_sum4<LB>(z0, z1, z2, blo, pg, pl, lane, red);
+	pfx_slot_sum4<LB>(z0, z1, z2, bhi, pg, pl, lane, red);
     }
     const float ts = am + as;
     const unsigned n_space = nb - nm;
@@ -1414,7 +1421,7 @@ __device__ __forceinline__ float pfx_round(const float *ring, unsigned R, unsign
 	as = fast_div(as, (float)n_space);
     const float other = one ? am : as;					/* :305-311 */
     float dv = own ? fast_div(fabsf(sig - other), other) : 0.f;
-    dv = pfx_slot_sum1<LB>(dv, pg, pl, lane);
+    dv = pfx_slot_sum1<LB>(dv, pg, pl, lane, red);
     const float divergence = dv * 2.f * geo.inv_n_bits;		/* :312-313 */
     if (!valid || tn == INFINITY) {					/* pass 1 reject, :211-212 */
 	bits_lo_out = bits_hi_out = 0u;
@@ -1437,7 +1444,7 @@ template <int LB>
 __device__ __forceinline__ Found pfx_search(const float *ring, unsigned R, unsigned base, unsigned r0,
 	const float4 *pre, const float4 *tot, const float4 *twc, const float4 *__restrict__ tw_sample,
 	const fsk_b200_pfx &pg, const fsk_b200_geom &geo, const PfxLane &pl, int sel, unsigned try_first,
-	const fsk_b200_pfx_kind &kd, float limit, unsigned lane, unsigned &ncand)
+	const fsk_b200_pfx_kind &kd, float limit, unsigned lane, float4 *red, unsigned &ncand)
 {
     const unsigned FULL = 0xffffffffu;
     const unsigned cpr = pg.cpr, k_dn = kd.k_dn, ncands = kd.ncands, step = kd.step;
@@ -1456,7 +1463,7 @@ __device__ __forceinline__ Found pfx_search(const float *ring, unsigned R, unsig
 	    t = try_first - (o >> 1) * step;
 	unsigned lo, hi;
 	float a;
-	float c = pfx_round<LB>(ring, R, base, r0, t, valid, pre, tot, twc, tw_sample, pg, geo, pl, sel, lane, lo, hi, a);
+	float c = pfx_round<LB>(ring, R, base, r0, t, valid, pre, tot, twc, tw_sample, pg, geo, pl, sel, lane, red, lo, hi, a);
 	if (!(c > 0.f))
 	    c = 0.f;					/* NaN and negatives never win (:492) */
 	ncand += min(cpr, ncands - o0);

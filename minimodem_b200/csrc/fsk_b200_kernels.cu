@@ -68,6 +68,7 @@ struct Smem {
     unsigned long long *bars;	/* two mbarriers per stream (bulk fill) */
     float4 *pre, *tot;		/* MODE 3: the stream's chunk-prefix table and its 32 lane-run totals */
     const float4 *loc;		/* MODE 3: the block's copy of fsk_b200_pfx.loc (8 float4) */
+    float4 *red;		/* MODE 3, packed candidate slots: 32 entries of reduction scratch per stream */
 };
 
 /* pad: floats of the ring's head mirrored behind its end (0: no mirror); pfx_chunks: MODE 3 table entries
@@ -75,7 +76,7 @@ struct Smem {
 template <int G>
 __device__ __forceinline__ Smem carve(float4 *smem, const fsk_b200_geom &geo,
 	const float4 *__restrict__ tw_global, unsigned tw_in_smem, unsigned ring_floats, unsigned pad,
-	unsigned pfx_chunks = 0, const float *pfx_loc = nullptr)
+	unsigned pfx_chunks = 0, const float *pfx_loc = nullptr, unsigned pfx_red = 0)
 {
     const unsigned N = geo.tw_entries, wpb = blockDim.x >> 5;	/* table entries staged (>= bit_nsamples) */
     Smem s;
@@ -106,8 +107,9 @@ __device__ __forceinline__ Smem carve(float4 *smem, const fsk_b200_geom &geo,
 	    reinterpret_cast<float *>(pfx)[threadIdx.x] = pfx_loc[threadIdx.x];
 	pfx += 8;
     }
-    s.pre = pfx + (size_t)slot * (pfx_chunks + 32u);
+    s.pre = pfx + (size_t)slot * (pfx_chunks + 32u + pfx_red);
     s.tot = s.pre + pfx_chunks;
+    s.red = s.tot + 32u;
     __syncthreads();
     return s;
 }
@@ -259,7 +261,7 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
     const unsigned ring_pad = MODE == 3 ? 4u * pg.S + 8u : (geo.bit_nsamples + 3u) & ~3u;
     constexpr int LB = W == 1 ? 0 : W;		/* MODE 3: log2 of the candidate slot (0: packed slots of any size) */
     const Smem sm = carve<G>(smem4, geo, tw_global, tw_in_smem, ring_floats, ring_pad, MODE == 3 ? 32u * pg.tstride : 0u,
-	    &pg.loc[0][0][0]);
+	    &pg.loc[0][0][0], (MODE == 3 && LB == 0) ? 32u : 0u);
     GROUP_VARS;
     const Ring rg = { smem_u32(sm.ring), ring_floats, ring_pad };
     const unsigned tw_s = tw_in_smem ? smem_u32(sm.tw) : 0u;	/* the fast path requires the table in shared memory */
@@ -267,7 +269,7 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
     const LaneWin<W> lw = lane_windows<G, W, L>(geo, g);
     const LaneWinM<W> lwm = lane_windows_multi<G, W, L>(geo, g);
     const PfxLane pfl = MODE == 3 ? pfx_lane(geo, pg, lane) : PfxLane();
-    const unsigned pre_s = smem_u32(sm.pre), tot_s = smem_u32(sm.tot), loc_s = smem_u32(sm.loc);
+    const unsigned pre_s = smem_u32(sm.pre), tot_s = smem_u32(sm.tot), loc_s = smem_u32(sm.loc), red_s = smem_u32(sm.red);
     const unsigned R = ring_floats;
 
     for (unsigned s = (blockIdx.x * wpb + warp) * spw + sidx; s < a.nstreams;
@@ -488,6 +490,7 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
 			float4 *tot = static_cast<float4 *>(__cvta_shared_to_generic(tot_s));
 			const float4 *twc = static_cast<const float4 *>(__cvta_shared_to_generic(tw_s));
 			const float4 *locp = static_cast<const float4 *>(__cvta_shared_to_generic(loc_s));
+			float4 *redp = static_cast<float4 *>(__cvta_shared_to_generic(red_s));
 			const unsigned base = pos_off & ~3u;
 			if (pass == 0) {
 			    if (pending) {
@@ -500,7 +503,7 @@ k_rx(const __grid_constant__ fsk_b200_geom geo, const __grid_constant__ fsk_b200
 			    __syncwarp(gmask);
 			}
 			f = pfx_search<LB>(ringp, R, base, pos_off & 3u, pre, tot, twc, tw_sample, pg, geo, pfl, which,
-				try_first, pg.kind[(carrier ? 1 : 0) + (pass ? 2 : 0)], limit, lane, ncand);
+				try_first, pg.kind[(carrier ? 1 : 0) + (pass ? 2 : 0)], limit, lane, redp, ncand);
 		    } else if (MODE == 2) {
 			/* :1265, :1378 from shared segment sums.  Which plan: the window is the one chosen at the
 			 * top of the iteration (carrier then), coarse or fine.  A coarse search in the steady
@@ -1679,7 +1682,8 @@ static int pick_shape(const CudaEngine *ce, const fsk_b200_geom *g, unsigned nee
 	const unsigned ring3 = ce->ring ? ring : ring_min;
 	const unsigned tw_stage = pf.fp + (pf.S + 2u) * pf.s4;	/* one period and a lane-run */
 	const size_t table = (size_t)tw_stage * sizeof(float4);
-	const size_t per_stream = ((size_t)ring3 + 4u * pf.S + 8u) * 4 + (size_t)nb * sizeof(float2) + 16 + (32u * (size_t)pf.tstride + 32u) * sizeof(float4);
+	const size_t per_stream = ((size_t)ring3 + 4u * pf.S + 8u) * 4 + (size_t)nb * sizeof(float2) + 16
+	    + (32u * (size_t)pf.tstride + 32u + (pf.pow2 ? 0u : 32u)) * sizeof(float4);	/* ring + mirror, scratch, barriers, table + totals (+ slot-sum scratch) */
 	/* warps (= streams) per block: the most resident streams per SM (each block pays the table and 1 KiB) */
 	const size_t sm_total = (size_t)ce->smem_optin + 1024;
 	int best_wpb = 0;

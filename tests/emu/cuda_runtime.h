@@ -306,6 +306,7 @@ static inline unsigned __ballot_sync(unsigned mask, int pred) { return emu::ball
 static inline unsigned __reduce_max_sync(unsigned mask, unsigned v) { return emu::reduce_max(mask, v); }
 static inline int __ffs(int v) { return __builtin_ffs(v); }
 static inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
+static inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
 template <class T>
 static inline T __ldg(const T *p) { return *p; }
 static inline void __trap() { emu::die("__trap()"); }
