@@ -595,6 +595,9 @@ def run_ours(a):
                 r = summarize(mm, torch, dist, world, dev, cwl, cfr, cst, ms_s, ms_k,
                               clean=not (awgn or offset), peak=peak)
                 r.update({"key": "%s_%s" % (key, suffix), "kernel": ceng.last_kernel(),
+                          # DRAM bytes of one launch of this workload's clean variant, if profiles/ holds an ncu
+                          # capture of it taken on this kernel source (else None)
+                          "traffic": None if (awgn or offset) else measured_traffic(mode, rate, cS, cn),
                           "workload": workload_name(mode, rate, cS, cn, ", amplitude %.2f%s%s" % (
                               amp, ", AWGN sigma %.2f" % awgn if awgn else "",
                               ", constant offset -%.2f (the reference's --Xrxnoise)" % offset if offset else "")),

@@ -59,3 +59,24 @@ def test_recorded_gpu_line_has_the_contract_keys():
     assert d["e2e"]["value"] < d["value"]                       # host buffers: PCIe-bound, not a copy of `value`
     assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
     assert "workload" in d["config"] and d["dtype"] == "f32" and d["data"] == "synthetic"
+
+
+def test_recorded_round2_line_carries_every_baseline_configuration():
+    """profiles/r2_bench_n1.json: the closing line of round 2 -- the headline with its ncu-backed traffic figure, and
+    the `configs` block with every other BASELINE configuration, each with kernel time, roofline fraction, the
+    kernel variant that ran and a decode check on >= 1 % of the streams."""
+    d = json.loads(open(os.path.join(ROOT, "profiles", "r2_bench_n1.json")).read().strip().splitlines()[-1])
+    r = d["roofline"]
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["frac"] >= 0.70          # the north star's bar
+    assert r["traffic"] and 0.99 < r["traffic"] / r["algorithmic_bytes"] < 1.01
+    assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    keys = [c["key"] for c in d["configs"]]
+    for want in ("cfg2_1200_awgn", "cfg3_rtty_8k", "cfg4_bell103_offset0.00", "cfg4_bell103_awgn0.50", "cfg5_same_per_gpu"):
+        assert any(k.startswith(want) for k in keys), (want, keys)
+    for c in d["configs"]:
+        assert c["value"] > 0 and 0 < c["roofline_frac"] < 1 and c["kernel_ms"] > 0 and c["kernel"].startswith("k_rx<")
+        assert c["decode_check"]["streams"] * 100 >= c["streams_per_gpu"]
+        if "awgn0.50" not in c["key"]:
+            assert c["decode_check"]["fraction_exact"] == 1.0, c["key"]
+    by = {c["key"]: c for c in d["configs"]}
+    assert "prefix-table" in by["cfg3_rtty_8k_clean"]["kernel"] and "prefix-table" in by["cfg4_bell103_offset0.00"]["kernel"]
