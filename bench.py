@@ -256,11 +256,37 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def _code_only(text):
+    """C/CUDA source without comments and without white space (string and character literals kept as they are):
+    what the compiler sees, so a comment edit does not cut an ncu figure loose from the build it was taken on."""
+    out, i, n = [], 0, len(text)
+    while i < n:
+        c = text[i]
+        if c == "/" and i + 1 < n and text[i + 1] == "*":
+            j = text.find("*/", i + 2)
+            i = n if j < 0 else j + 2
+            out.append(" ")
+        elif c == "/" and i + 1 < n and text[i + 1] == "/":
+            j = text.find("\n", i)
+            i = n if j < 0 else j
+        elif c in "\"'":
+            j = i + 1
+            while j < n and text[j] != c:
+                j += 2 if text[j] == "\\" else 1
+            out.append(text[i:j + 1])
+            i = j + 1
+        else:
+            out.append(c)
+            i += 1
+    return " ".join("".join(out).split())
+
+
 def kernel_source_hash():
-    """sha256 over the CUDA sources of the rx kernel: ties an ncu DRAM-traffic figure to the build."""
+    """sha256 over the CUDA sources of the rx kernel, comments and white space removed: ties an ncu DRAM-traffic
+    figure to the build."""
     h = hashlib.sha256()
     for f in ("fsk_b200_kernels.cu", "fsk_b200_device.cuh", "fsk_b200_internal.h"):
-        h.update(open(os.path.join(ROOT, "minimodem_b200", "csrc", f), "rb").read())
+        h.update(_code_only(open(os.path.join(ROOT, "minimodem_b200", "csrc", f), encoding="utf-8", errors="replace").read()).encode())
     return h.hexdigest()[:16]
 
 

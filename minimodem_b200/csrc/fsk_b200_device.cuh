@@ -1,7 +1,7 @@
 /*
  * fsk_b200_device.cuh -- device functions of the B200 FSK engine.
  *
- * Two implementations of the same arithmetic:
+ * Two basic implementations of the same arithmetic:
  *
  *  FAST   frame_analyze_fast<G,W,L> / find_frame_fast: the stream's samples are in a
  *         per-stream shared-memory ring of R floats (R % 4 == 0) whose first
@@ -15,6 +15,10 @@
  *         memory, run-time window split, IEEE sqrt/div, the reference's serial
  *         summation order, fp64 folding of the fp32 partial sums for very long
  *         windows.  Used when the windows do not fit shared memory (e.g. 0.5 baud).
+ *
+ * On top of FAST: MULTI (find_frame_multi: the candidates of a search from shared segment sums),
+ * the sliding fine search (find_frame_slide) and PREFIX (pfx_build / pfx_round / pfx_search: every
+ * candidate of a loop iteration from one chunk-prefix table; one stream per warp).
  *
  * All floating-point steps that decide anything follow the reference's order
  * (src/fsk.c:107-174, :178-446, :449-538); comments carry its line numbers.

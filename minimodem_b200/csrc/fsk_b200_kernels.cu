@@ -19,8 +19,17 @@
  *     (src/fsk.c:477-502) and the rx-loop state machine (src/minimodem.c:1229-1407)
  *     run per group in registers.
  *
- * k_rx<G,W,L,MODE,FILL>   the whole rx loop per stream (MODE 0 fast / 1 generic)
- * k_rx_ws<G,W,L>          the same, warp-synchronous (selectable, measured slower)
+ *   - MODE 2 (shared segments) correlates every sample once per batch of up to three candidates;
+ *     MODE 3 (chunk-prefix table, the default for bit periods >= 128 samples) runs one stream per
+ *     warp, demodulates the whole search span ONCE per loop iteration into per-chunk prefix sums
+ *     (FFMA2, bank-conflict-free odd lane-runs, TMA bulk fill) and analyses every candidate of the
+ *     coarse and the fine search from that table, two or three candidates side by side.
+ *
+ * k_rx<G,W,L,MODE,FILL,SRC> the whole rx loop per stream: MODE 0 per candidate (the headline kernel at
+ *                         1200 baud), 1 generic (global memory, IEEE, serial order), 2 shared segments,
+ *                         3 prefix table (G = 32; W codes the candidate slot); FILL 0 cp.async, 1 TMA bulk
+ *                         copies; SRC 0 float32 rows, 1 int16 PCM rows widened inside the fill
+ * k_rx_ws<G,W,L>          MODE 0, warp-synchronous (selectable, measured slower)
  * k_find_frame<G,W,L,MODE> batched fsk_find_frame
  * k_tx, k_band_mags, k_detect_carrier, k_s16_to_f32, k_decode<KIND>   the "next" rows
  *
