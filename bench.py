@@ -108,7 +108,10 @@ def cpu_measure(mode, x, nsamples, nstreams, steps, warmup, want_port=False):
     copy is its own memory) through a persistent pool of pinned workers (orc.RxPool: one plan per
     worker built once, contiguous stream blocks first-touched by their worker).  The thread count is
     chosen by one untimed pass each at all / half of the allowed CPUs; then `warmup` untimed and
-    `steps` timed passes.  `value` is the MEDIAN pass, `best` the fastest one.
+    `steps` timed passes.  `value` is the FASTEST pass, `median` the median one: on the shared hosts of the pool a
+    pass of the same work lands either at ~0.30 s or at ~0.39 s, so a median of three or five flips between the two
+    (4.1-5.1 Gsamples/s from run to run) while the minimum reproduces within 2 % -- and it is the conservative
+    choice for every speed-up quoted against this arm.
 
     kind "reference" = the unmodified src/fsk.c.  Its speed is its FFT library's: it is timed on
     MKL's DFTI (oracle/_ref/libfsk_ref_dfti.so, the closest thing to FFTW in this image; not
@@ -152,13 +155,13 @@ def cpu_measure(mode, x, nsamples, nstreams, steps, warmup, want_port=False):
             check = sig
         med, best = float(np.median(ts)), float(min(ts))
         nsam = nstreams * nsamples
-        out[k] = dict(value=nsam / med / 1e6, best=nsam / best / 1e6, unit="Msamples/s", cores=nt, kind=k,
-                      passes=len(ts), seconds_per_pass=med, seconds_best_pass=best,
+        out[k] = dict(value=nsam / best / 1e6, best=nsam / best / 1e6, median=nsam / med / 1e6, unit="Msamples/s",
+                      cores=nt, kind=k, passes=len(ts), seconds_per_pass=best, seconds_median_pass=med, seconds_best_pass=best,
                       seconds_all_passes=[round(t, 4) for t in ts],
                       sample="%d streams x %d samples per pass (%d distinct streams, each copy its own memory); "
                              "persistent pool of %d pinned threads (best of {%d, %d}), plans built once outside the "
                              "timed passes, contiguous per-thread stream blocks first-touched by their thread; "
-                             "value = median of %d passes; %s" % (
+                             "value = fastest of %d passes (median reported beside it); %s" % (
                                  nstreams, nsamples, x.shape[0], nt, cores, max(1, cores // 2), len(ts),
                                  "unmodified src/fsk.c (oracle/_ref) on the %s, behind the oracle rx loop" % fft
                                  if k == "reference" else "oracle port (two-bin direct DFT, no FFT): best-case CPU"),
@@ -581,7 +584,7 @@ def run_ours(a):
             import orc
             ncpu = cpu_sample_streams(a)
             hostx = np.ascontiguousarray(x[:min(128, S), :n].cpu().numpy())
-            cpu, both = cpu_measure(orc.Mode(a.mode, sample_rate=a.rate), hostx, n, ncpu, steps=3, warmup=1,
+            cpu, both = cpu_measure(orc.Mode(a.mode, sample_rate=a.rate), hostx, n, ncpu, steps=5, warmup=1,
                                     want_port=True)
             cpu_best = both.get("port") if both.get("port") is not cpu else None
         except Exception as ex:  # the checker is optional for the number, never for the tests
